@@ -69,6 +69,36 @@ int kws_frontend_stream(kws_frontend_t* fe, const int16_t* d_pcm, int64_t total_
                         int hop_samples, int64_t first_window, int64_t n_windows, float out_scale,
                         float* d_out_f32, void* d_scratch, int scratch_ready, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Embedding tower — replaces `tf.keras.models.load_model(base)` + `Model(inputs,
+ * base.get_layer("dense_2").output)` + `.predict(specs)` (multilingual_kws/embedding/
+ * transfer_learning.py:36-43, distance_filtering.py:12-27,55,69; architecture defined at
+ * multilingual_kws/train_multilingual_embedding.py:66-83 = Keras EfficientNetB0 + GAP + 3 Dense).
+ * `blob` is the "KWSW0001" container of Keras-named fp32 tensors (multilingual_kws_b200/model.py
+ * writes it).  BatchNorm is folded at create time (inference mode, as every reference forward outside
+ * pre-training).  Activations are bf16 with fp32 accumulation; output is fp32 [batch, out_dim].
+ * ------------------------------------------------------------------------------------------- */
+int kws_embed_create(kws_embed_t** out, const void* blob, size_t bytes);
+void kws_embed_destroy(kws_embed_t* m);
+int kws_embed_info(const kws_embed_t* m, int* in_h, int* in_w, int* out_dim, int* n_ops, double* flops_per_clip);
+int kws_embed_op_name(const kws_embed_t* m, int op, char* buf, size_t buf_bytes, int64_t* out_elems_per_clip);
+/* clips per pass through the layer list (keeps one chunk's activations L2-resident) */
+int kws_embed_set_chunk(kws_embed_t* m, int chunk);
+size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch);
+/* d_feats fp32 [batch, 49, 40] (the frontend's output) -> d_emb fp32 [batch, out_dim] */
+int kws_embed_forward(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
+                      size_t ws_bytes, void* stream);
+/* same, additionally copying the output of op `tap_op` (bf16 NHWC; fp32 for the last op) to d_tap */
+int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
+                          size_t ws_bytes, int tap_op, void* d_tap, void* stream);
+
+/* The pointwise-conv / dense operator on its own (tcgen05 GEMM + fused epilogue):
+ * out[M,N] = act(A[M,K] x W[N,K]^T + bias[N]) (+ residual[M,N]); A, W, residual bf16 K-major; out bf16
+ * or fp32; act 0 none, 1 swish, 2 relu, 3 selu; gap4 averages aligned groups of 4 rows (out [M/4,N]);
+ * block_n 0 = automatic.  N and K must be multiples of 8. */
+int kws_gemm_bf16(const void* d_a, const void* d_w, int M, int N, int K, const float* d_bias, int act,
+                  const void* d_residual, void* d_out, int out_f32, int gap4, int block_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

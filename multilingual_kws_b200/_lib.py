@@ -26,6 +26,17 @@ SIGNATURES = {
     "kws_frontend_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "kws_frontend_stream_num_windows": (c_int64, [c_void_p, c_int64, c_int, c_int]),
     "kws_frontend_stream_scratch_bytes": (c_size_t, [c_void_p, c_int64]),
+    "kws_embed_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_size_t]),
+    "kws_embed_destroy": (None, [c_void_p]),
+    "kws_embed_info": (c_int, [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+                               ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double)]),
+    "kws_embed_op_name": (c_int, [c_void_p, c_int, ctypes.c_char_p, c_size_t, ctypes.POINTER(c_int64)]),
+    "kws_embed_set_chunk": (c_int, [c_void_p, c_int]),
+    "kws_embed_workspace_bytes": (c_size_t, [c_void_p, c_int]),
+    "kws_embed_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kws_embed_forward_tap": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
+    "kws_gemm_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                              c_int, c_void_p]),
     "kws_frontend_stream": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_int64, c_float, c_void_p,
                                     c_void_p, c_int, c_void_p]),
 }

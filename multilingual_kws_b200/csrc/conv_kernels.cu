@@ -1,0 +1,285 @@
+// conv_kernels.cu — the non-GEMM kernels of the EfficientNet-B0 embedding tower (sm_100a):
+//   stem_conv_kernel   Rescaling(1/255) + ZeroPadding2D(correct_pad) + Conv3x3 s2 (1->32) + BN + swish,
+//                      fp32 log-mel features in, NHWC bf16 out.
+//   dwse_kernel        one MBConv middle section per launch: depthwise kxk conv (TF SAME / correct_pad+VALID)
+//                      + folded BN + swish + squeeze-excite (global pool -> FC+swish -> FC+sigmoid -> scale),
+//                      whole clips staged in shared memory by TMA bulk copies; the pooled vector never
+//                      leaves the SM, the gated activation is written once as the next GEMM's A operand.
+// Replaces the cuDNN depthwise / Eigen kernels behind Keras' EfficientNetB0 block()
+// (model defined at reference multilingual_kws/train_multilingual_embedding.py:66-83).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.h"
+#include "conv_kernels.h"
+#include "ptx.cuh"
+
+namespace kws {
+
+namespace {
+
+__device__ __forceinline__ float swish(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// ---------------------------------------------------------------- stem
+constexpr int kStemThreads = 256;
+constexpr int kStemC = 32;
+
+__global__ void __launch_bounds__(kStemThreads)
+stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  float* s_in = reinterpret_cast<float*>(smem);                     // [H*W]
+  float* s_w = s_in + ((P.H * P.W + 3) & ~3);                        // [9][32]
+  float* s_b = s_w + 9 * kStemC;                                     // [32]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 9 * kStemC; i += kStemThreads) s_w[i] = P.w[i];
+  if (tid < kStemC) s_b[tid] = P.bias[tid];
+  const int npix = P.Ho * P.Wo;
+  for (int clip = blockIdx.x; clip < batch; clip += gridDim.x) {
+    __syncthreads();
+    const float* src = feats + (size_t)clip * P.H * P.W;
+    for (int i = tid; i < P.H * P.W; i += kStemThreads) s_in[i] = fmaf(__ldg(src + i), P.in_scale, P.in_shift);
+    __syncthreads();
+    // item = (pixel, group of 8 output channels)
+    for (int item = tid; item < npix * 4; item += kStemThreads) {
+      const int p = item >> 2, g = item & 3;
+      const int ho = p / P.Wo, wo = p - ho * P.Wo;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = s_b[g * 8 + j];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int r = ho * 2 + kh - P.pad_top;
+        if (r < 0 || r >= P.H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int c = wo * 2 + kw - P.pad_left;
+          if (c < 0 || c >= P.W) continue;
+          const float x = s_in[r * P.W + c];
+          const float* wv = s_w + (kh * 3 + kw) * kStemC + g * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, wv[j], acc[j]);
+        }
+      }
+      uint4 pk;
+      pk.x = pack_bf16x2(swish(acc[0]), swish(acc[1]));
+      pk.y = pack_bf16x2(swish(acc[2]), swish(acc[3]));
+      pk.z = pack_bf16x2(swish(acc[4]), swish(acc[5]));
+      pk.w = pack_bf16x2(swish(acc[6]), swish(acc[7]));
+      *reinterpret_cast<uint4*>(out + ((size_t)clip * npix + p) * kStemC + g * 8) = pk;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- depthwise + SE
+constexpr int kDwThreads = 256;
+
+struct DwSmem {
+  uint32_t in_bytes, out_off, pooled_off, s_off, bar_off, total;
+};
+__host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
+  DwSmem L;
+  L.in_bytes = (uint32_t)G * P.H * P.W * P.C * 2;
+  L.out_off = (L.in_bytes + 127) & ~127u;
+  L.pooled_off = L.out_off + (((uint32_t)G * P.Ho * P.Wo * P.C * 2 + 127) & ~127u);
+  L.s_off = L.pooled_off + (uint32_t)G * P.C * 4;
+  L.bar_off = (L.s_off + (uint32_t)G * P.se * 4 + 15) & ~15u;
+  L.total = L.bar_off + 16;
+  return L;
+}
+
+template <int K, int S>
+__global__ void __launch_bounds__(kDwThreads)
+dwse_kernel(const __nv_bfloat16* __restrict__ x, int batch, int G, DwseParams P, __nv_bfloat16* __restrict__ y) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const DwSmem L = dw_smem(P, G);
+  const uint32_t* s_in = reinterpret_cast<const uint32_t*>(smem);              // bf16x2 words, [G][H][W][C/2]
+  uint32_t* s_out = reinterpret_cast<uint32_t*>(smem + L.out_off);            // bf16x2, [G][Ho*Wo][C/2]
+  float* s_pool = reinterpret_cast<float*>(smem + L.pooled_off);              // [G][C] sums, later gates
+  float* s_se = reinterpret_cast<float*>(smem + L.s_off);                     // [G][se]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = P.C, C2 = C >> 1, npix = P.Ho * P.Wo;
+  const int clip_words = P.H * P.W * C2;
+  const float inv_npix = 1.0f / (float)npix;
+
+  if (tid == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  // thread -> (channel pair, pixel lane)
+  const int PL = C2 >= kDwThreads ? 1 : kDwThreads / C2;
+  const int cp0 = C2 >= kDwThreads ? tid : tid % C2;
+  const int pl = C2 >= kDwThreads ? 0 : tid / C2;
+  const bool active = pl < PL;
+  uint32_t parity = 0;
+
+  const int n_groups = (batch + G - 1) / G;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int g0 = grp * G;
+    const int gn = min(G, batch - g0);
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)gn * clip_words * 4;
+      ptx::mbar_expect_tx(bar, bytes);
+      ptx::tma_bulk_g2s(smem, x + (size_t)g0 * clip_words * 2, bytes, bar);
+    }
+    for (int i = tid; i < gn * C; i += kDwThreads) s_pool[i] = 0.0f;
+    ptx::mbar_wait(bar, parity);
+    parity ^= 1;
+    __syncthreads();
+
+    // ---- depthwise conv + BN + swish -> s_out (bf16), channel sums -> s_pool
+    if (active) {
+      for (int cp = cp0; cp < C2; cp += kDwThreads) {
+        float2 wreg[K * K];
+#pragma unroll
+        for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp);
+        const float2 bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp);
+        for (int g = 0; g < gn; ++g) {
+          const uint32_t* in_g = s_in + (size_t)g * clip_words + cp;
+          float sum0 = 0.0f, sum1 = 0.0f;
+          for (int p = pl; p < npix; p += PL) {
+            const int ho = p / P.Wo, wo = p - ho * P.Wo;
+            float a0 = bias.x, a1 = bias.y;
+#pragma unroll
+            for (int kh = 0; kh < K; ++kh) {
+              const int r = ho * S + kh - P.pad_top;
+              if (r < 0 || r >= P.H) continue;
+#pragma unroll
+              for (int kw = 0; kw < K; ++kw) {
+                const int c = wo * S + kw - P.pad_left;
+                if (c < 0 || c >= P.W) continue;
+                const uint32_t v = in_g[(r * P.W + c) * C2];
+                a0 = fmaf(bf_lo(v), wreg[kh * K + kw].x, a0);
+                a1 = fmaf(bf_hi(v), wreg[kh * K + kw].y, a1);
+              }
+            }
+            a0 = swish(a0);
+            a1 = swish(a1);
+            sum0 += a0;
+            sum1 += a1;
+            s_out[((size_t)g * npix + p) * C2 + cp] = pack_bf16x2(a0, a1);
+          }
+          if (PL == 1) {
+            s_pool[g * C + 2 * cp] = sum0;
+            s_pool[g * C + 2 * cp + 1] = sum1;
+          } else {
+            atomicAdd(&s_pool[g * C + 2 * cp], sum0);
+            atomicAdd(&s_pool[g * C + 2 * cp + 1], sum1);
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- SE reduce: s[g][j] = swish(b1[j] + mean_g . w1[j][:]); one warp per j, weights read once per group
+    for (int j = warp; j < P.se; j += kDwThreads / 32) {
+      const float* wrow = P.w_se1 + (size_t)j * C;
+      for (int gb = 0; gb < gn; gb += 8) {          // register-block 8 clips per pass over the weight row
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.0f;
+        for (int c = lane; c < C; c += 32) {
+          const float wv = __ldg(wrow + c);
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (gb + u < gn) acc[u] = fmaf(wv, s_pool[(gb + u) * C + c], acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float a = acc[u];
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          if (lane == 0 && gb + u < gn) s_se[(gb + u) * P.se + j] = swish(a * inv_npix + __ldg(P.b_se1 + j));
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- SE expand: gate[g][c] = sigmoid(b2[c] + s[g] . w2[:][c])  (overwrites the pooled sums)
+    for (int c = tid; c < C; c += kDwThreads) {
+      const float b2 = __ldg(P.b_se2 + c);
+      for (int gb = 0; gb < gn; gb += 8) {
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = b2;
+        for (int j = 0; j < P.se; ++j) {
+          const float wv = __ldg(P.w_se2 + (size_t)j * C + c);
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (gb + u < gn) acc[u] = fmaf(wv, s_se[(gb + u) * P.se + j], acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (gb + u < gn) s_pool[(gb + u) * C + c] = sigmoidf(acc[u]);
+      }
+    }
+    __syncthreads();
+
+    // ---- scale and store (coalesced 4-byte words; the whole group is one contiguous block of y)
+    {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(y) + (size_t)g0 * npix * C2;
+      const int words = gn * npix * C2;
+      for (int i = tid; i < words; i += kDwThreads) {
+        const int g = i / (npix * C2);
+        const int cpair = i % C2;
+        const uint32_t v = s_out[i];
+        const float2 gate = *reinterpret_cast<const float2*>(&s_pool[g * C + 2 * cpair]);
+        dst[i] = pack_bf16x2(bf_lo(v) * gate.x, bf_hi(v) * gate.y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int launch_stem(const float* d_feats, int batch, const StemParams& P, __nv_bfloat16* d_out, int sm_count,
+                cudaStream_t st) {
+  if (batch == 0) return KWS_OK;
+  const size_t smem = (size_t)(((P.H * P.W + 3) & ~3) + 9 * kStemC + kStemC) * 4;
+  const int grid = batch < sm_count * 4 ? batch : sm_count * 4;
+  stem_conv_kernel<<<grid, kStemThreads, smem, st>>>(d_feats, batch, P, d_out);
+  KWS_CUDA_CHECK(cudaGetLastError());
+  return KWS_OK;
+}
+
+int dwse_pick_group(const DwseParams& P, int max_smem) {
+  // Largest G in {16,8,4,2,1} whose working set allows >= 2 CTAs per SM; else the largest that fits at all.
+  const int cands[5] = {16, 8, 4, 2, 1};
+  for (int i = 0; i < 5; ++i)
+    if ((int)dw_smem(P, cands[i]).total <= 100 * 1024) return cands[i];
+  for (int i = 0; i < 5; ++i)
+    if ((int)dw_smem(P, cands[i]).total <= max_smem) return cands[i];
+  return 0;
+}
+
+int launch_dwse(const __nv_bfloat16* d_x, int batch, const DwseParams& P, __nv_bfloat16* d_y, int G, int sm_count,
+                cudaStream_t st) {
+  if (batch == 0) return KWS_OK;
+  KWS_REQUIRE(G >= 1, "dwse: layer does not fit shared memory");
+  KWS_REQUIRE(P.C % 8 == 0, "dwse: channels must be a multiple of 8");
+  KWS_REQUIRE((P.K == 3 || P.K == 5) && (P.S == 1 || P.S == 2), "dwse: unsupported kernel %d / stride %d", P.K, P.S);
+  const size_t smem = dw_smem(P, G).total;
+  void (*kern)(const __nv_bfloat16*, int, int, DwseParams, __nv_bfloat16*) =
+      P.K == 3 ? (P.S == 1 ? dwse_kernel<3, 1> : dwse_kernel<3, 2>) : (P.S == 1 ? dwse_kernel<5, 1> : dwse_kernel<5, 2>);
+  KWS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_groups = (batch + G - 1) / G;
+  const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+  const int grid = n_groups < sm_count * per_sm ? n_groups : sm_count * per_sm;
+  kern<<<grid, kDwThreads, smem, st>>>(d_x, batch, G, P, d_y);
+  KWS_CUDA_CHECK(cudaGetLastError());
+  return KWS_OK;
+}
+
+}  // namespace kws

@@ -1,0 +1,30 @@
+// conv_kernels.h — launchers for the stem and depthwise+SE kernels (see conv_kernels.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace kws {
+
+struct StemParams {
+  int H, W, Ho, Wo, pad_top, pad_left;
+  float in_scale, in_shift;   // Rescaling(1/255) + Normalization: x' = x*in_scale + in_shift
+  const float* w;      // [9][32]  conv kernel * BN scale   (device)
+  const float* bias;   // [32]     folded BN shift
+};
+
+struct DwseParams {
+  int H, W, C, Ho, Wo, K, S, pad_top, pad_left, se;
+  const float* w_dw;   // [K*K][C]  depthwise kernel * BN scale
+  const float* b_dw;   // [C]       folded BN shift
+  const float* w_se1;  // [se][C]   se_reduce kernel (transposed)
+  const float* b_se1;  // [se]
+  const float* w_se2;  // [se][C]   se_expand kernel
+  const float* b_se2;  // [C]
+};
+
+int launch_stem(const float* d_feats, int batch, const StemParams& P, __nv_bfloat16* d_out, int sm_count, cudaStream_t st);
+int dwse_pick_group(const DwseParams& P, int max_smem);
+int launch_dwse(const __nv_bfloat16* d_x, int batch, const DwseParams& P, __nv_bfloat16* d_y, int G, int sm_count,
+                cudaStream_t st);
+
+}  // namespace kws

@@ -1,0 +1,496 @@
+// embed.cu — the EfficientNet-B0 embedding tower as a native runtime object (C ABI kws_embed_*).
+//
+// Replaces `base_model = tf.keras.models.load_model(...)` + `Model(inputs, get_layer("dense_2").output)`
+// + `.predict(...)` of the reference (multilingual_kws/embedding/transfer_learning.py:36-43,
+// distance_filtering.py:12-27; architecture train_multilingual_embedding.py:66-83).
+//
+// At create time the Keras-named fp32 weights are folded for inference (BatchNorm -> scale/shift of the
+// preceding conv, eps 1e-3), converted to the layouts the kernels want (K-major bf16 for every tensor-core
+// contraction, fp32 for depthwise / SE / biases) and uploaded once.  A forward pass is a fixed list of
+// launches on the caller's stream: stem conv, then per MBConv block
+//   [expand 1x1 GEMM + BN + swish] -> [depthwise + BN + swish + SE, fused] -> [project 1x1 GEMM + BN (+ residual)]
+// then top 1x1 GEMM + BN + swish + 2x2 average pool (fused epilogue) and the three dense GEMMs.
+// Activations are NHWC bf16 in three ping-pong workspace buffers; the batch is walked in chunks so
+// one chunk's inter-layer activations stay resident in the 126 MB L2.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "conv_kernels.h"
+#include "gemm_tcgen05.cuh"
+
+using namespace kws;
+
+namespace {
+
+struct HostTensor {
+  std::vector<uint32_t> dims;
+  const float* data = nullptr;
+  size_t size = 0;
+};
+typedef std::map<std::string, HostTensor> WeightMap;
+
+// container: "KWSW0001", u32 n; per entry: u32 name_len, name (padded to 4), u32 ndim, u32 dims[], f32 data[]
+bool parse_blob(const void* blob, size_t bytes, WeightMap* out, std::string* err) {
+  const uint8_t* p = static_cast<const uint8_t*>(blob);
+  const uint8_t* end = p + bytes;
+  if (bytes < 12 || memcmp(p, "KWSW0001", 8) != 0) { *err = "bad magic"; return false; }
+  p += 8;
+  uint32_t n;
+  memcpy(&n, p, 4); p += 4;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (p + 4 > end) { *err = "truncated"; return false; }
+    uint32_t nl; memcpy(&nl, p, 4); p += 4;
+    const uint32_t nlp = (nl + 3) & ~3u;
+    if (p + nlp + 4 > end) { *err = "truncated"; return false; }
+    std::string name(reinterpret_cast<const char*>(p), nl); p += nlp;
+    uint32_t nd; memcpy(&nd, p, 4); p += 4;
+    if (nd > 8 || p + 4 * nd > end) { *err = "bad ndim for " + name; return false; }
+    HostTensor t;
+    t.size = 1;
+    for (uint32_t d = 0; d < nd; ++d) { uint32_t v; memcpy(&v, p, 4); p += 4; t.dims.push_back(v); t.size *= v; }
+    if (p + 4 * t.size > end) { *err = "truncated data for " + name; return false; }
+    t.data = reinterpret_cast<const float*>(p);
+    p += 4 * t.size;
+    (*out)[name] = t;
+  }
+  return true;
+}
+
+struct BlockCfg { int k, reps, fin, fout, e, s; };
+const BlockCfg kStages[7] = {{3, 1, 32, 16, 1, 1}, {3, 2, 16, 24, 6, 2}, {5, 2, 24, 40, 6, 2}, {3, 3, 40, 80, 6, 2},
+                             {5, 3, 80, 112, 6, 1}, {5, 4, 112, 192, 6, 2}, {3, 1, 192, 320, 6, 1}};
+const float kBnEps = 1e-3f;
+
+enum OpKind { kOpStem, kOpGemm, kOpDwse };
+
+struct Op {
+  OpKind kind;
+  std::string name;            // Keras layer whose output this op produces (for taps)
+  int in_buf, out_buf;         // 0 = X, 1 = E, 2 = D, -1 = external (features / embedding)
+  int res_buf = -1;
+  // geometry
+  int rows_per_clip = 0;       // GEMM: M = rows_per_clip * batch
+  int N = 0, K = 0;
+  int act = 0, gap4 = 0, out_f32 = 0;
+  const __nv_bfloat16* w = nullptr;   // GEMM weights [N][K]
+  const float* bias = nullptr;
+  StemParams stem{};
+  DwseParams dw{};
+  int dw_group = 1;
+  size_t out_elems_per_clip = 0;
+};
+
+}  // namespace
+
+struct kws_embed {
+  int H = 49, W = 40, out_dim = 0;
+  float in_scale = 1.0f / 255.0f, in_shift = 0.0f;
+  std::vector<Op> ops;
+  std::vector<void*> dev_allocs;
+  size_t buf_elems[3] = {0, 0, 0};     // per clip, bf16 elements
+  int sm_count = 0, max_smem = 0;
+  int chunk = 256;
+  double flops_per_clip = 0;
+};
+
+namespace {
+
+template <typename T>
+T* upload(kws_embed* m, const std::vector<T>& h, cudaError_t* err) {
+  T* d = nullptr;
+  *err = cudaMalloc(&d, h.size() * sizeof(T));
+  if (*err != cudaSuccess) return nullptr;
+  m->dev_allocs.push_back(d);
+  *err = cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return d;
+}
+
+struct Builder {
+  kws_embed* m;
+  const WeightMap& w;
+  std::string err;
+  cudaError_t cerr = cudaSuccess;
+
+  const HostTensor* get(const std::string& name, size_t expect) {
+    auto it = w.find(name);
+    if (it == w.end()) { err = "missing weight " + name; return nullptr; }
+    if (it->second.size != expect) { err = "wrong size for " + name; return nullptr; }
+    return &it->second;
+  }
+  // BN inference fold: y = x*scale + shift
+  bool bn(const std::string& name, int c, std::vector<float>* scale, std::vector<float>* shift) {
+    const HostTensor *g = get(name + "/gamma", c), *b = get(name + "/beta", c), *mu = get(name + "/moving_mean", c),
+                     *var = get(name + "/moving_variance", c);
+    if (!g || !b || !mu || !var) return false;
+    scale->resize(c); shift->resize(c);
+    for (int i = 0; i < c; ++i) {
+      const float s = g->data[i] / sqrtf(var->data[i] + kBnEps);
+      (*scale)[i] = s;
+      (*shift)[i] = b->data[i] - mu->data[i] * s;
+    }
+    return true;
+  }
+  // 1x1 conv / dense kernel [K][N] (Keras) -> bf16 [N][K] with per-output scale
+  const __nv_bfloat16* gemm_weight(const std::string& name, int K, int N, const std::vector<float>* scale) {
+    const HostTensor* t = get(name, (size_t)K * N);
+    if (!t) return nullptr;
+    std::vector<__nv_bfloat16> h((size_t)N * K);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) h[(size_t)n * K + k] = __float2bfloat16(t->data[(size_t)k * N + n] * (scale ? (*scale)[n] : 1.0f));
+    return upload(m, h, &cerr);
+  }
+  const float* vec(const std::vector<float>& v) { return upload(m, v, &cerr); }
+};
+
+int pick_block_n(int N, int m_tiles, int sm_count) {
+  // candidates with little column padding; prefer the largest that still gives every SM a tile
+  const int cands[] = {256, 240, 224, 192, 160, 144, 128, 112, 96, 80, 64, 48, 32, 16};
+  int best = -1;
+  for (int bn : cands) {
+    const int n_tiles = (N + bn - 1) / bn;
+    if (n_tiles * bn - N >= 16 && bn > 16) continue;          // wasteful padding
+    if (best < 0) best = bn;
+    if ((long long)n_tiles * m_tiles >= sm_count) return bn;
+    if (bn <= 64) break;                                       // do not shrink tiles below 64 columns
+    best = bn;
+  }
+  return best > 0 ? best : 16;
+}
+
+}  // namespace
+
+extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t bytes) {
+  KWS_REQUIRE(out && blob, "kws_embed_create: NULL argument");
+  *out = nullptr;
+  WeightMap wm;
+  std::string perr;
+  if (!parse_blob(blob, bytes, &wm, &perr)) {
+    set_error("kws_embed_create: weight container: %s", perr.c_str());
+    return KWS_ERR_ARG;
+  }
+  int dev = 0;
+  kws_embed* m = new (std::nothrow) kws_embed();
+  KWS_REQUIRE(m != nullptr, "out of host memory");
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) {
+    set_error("kws_embed_create: CUDA device required (%s); there is no CPU fallback", cudaGetErrorString(e));
+    delete m;
+    return KWS_ERR_CUDA;
+  }
+  Builder B{m, wm};
+  auto fail = [&](int code) {
+    if (B.cerr != cudaSuccess) set_error("kws_embed_create: %s", cudaGetErrorString(B.cerr));
+    else set_error("kws_embed_create: %s", B.err.c_str());
+    for (void* p : m->dev_allocs) cudaFree(p);
+    delete m;
+    return code;
+  };
+#define CK(x) do { if (!(x) || B.cerr != cudaSuccess) return fail(B.cerr != cudaSuccess ? KWS_ERR_CUDA : KWS_ERR_ARG); } while (0)
+
+  // Rescaling(1/255) + Normalization(mean, var)
+  {
+    auto itm = wm.find("normalization/mean"), itv = wm.find("normalization/variance");
+    float mean = 0.f, var = 1.f;
+    if (itm != wm.end() && itm->second.size >= 1) mean = itm->second.data[0];
+    if (itv != wm.end() && itv->second.size >= 1) var = itv->second.data[0];
+    const float sd = fmaxf(sqrtf(var), 1e-7f);
+    m->in_scale = 1.0f / (255.0f * sd);
+    m->in_shift = -mean / sd;
+  }
+  int h = m->H, w = m->W;
+  double macs = 0;
+  // ---- stem
+  {
+    std::vector<float> sc, sh;
+    CK(B.bn("stem_bn", 32, &sc, &sh));
+    const HostTensor* k = B.get("stem_conv/kernel", 9 * 32);
+    CK(k);
+    std::vector<float> wf(9 * 32);
+    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < 32; ++c) wf[t * 32 + c] = k->data[t * 32 + c] * sc[c];
+    Op op;
+    op.kind = kOpStem; op.name = "stem_activation"; op.in_buf = -1; op.out_buf = 0;
+    op.stem.H = h; op.stem.W = w;
+    op.stem.pad_top = 1 - (1 - h % 2); op.stem.pad_left = 1 - (1 - w % 2);
+    op.stem.Ho = (h + op.stem.pad_top + 1 - 3) / 2 + 1;
+    op.stem.Wo = (w + op.stem.pad_left + 1 - 3) / 2 + 1;
+    op.stem.in_scale = m->in_scale; op.stem.in_shift = m->in_shift;
+    op.stem.w = B.vec(wf); op.stem.bias = B.vec(sh);
+    CK(op.stem.w && op.stem.bias);
+    h = op.stem.Ho; w = op.stem.Wo;
+    op.out_elems_per_clip = (size_t)h * w * 32;
+    macs += (double)h * w * 32 * 9;
+    m->ops.push_back(op);
+  }
+  // ---- MBConv blocks
+  for (int si = 0; si < 7; ++si) {
+    for (int r = 0; r < kStages[si].reps; ++r) {
+      const BlockCfg& c = kStages[si];
+      const std::string n = "block" + std::to_string(si + 1) + std::string(1, (char)('a' + r));
+      const int stride = r == 0 ? c.s : 1;
+      const int cin = r == 0 ? c.fin : c.fout;
+      const int cexp = cin * c.e, cout = c.fout;
+      const int se = cin / 4 > 1 ? cin / 4 : 1;
+      if (c.e != 1) {
+        std::vector<float> sc, sh;
+        CK(B.bn(n + "_expand_bn", cexp, &sc, &sh));
+        Op op;
+        op.kind = kOpGemm; op.name = n + "_expand_activation"; op.in_buf = 0; op.out_buf = 1;
+        op.rows_per_clip = h * w; op.N = cexp; op.K = cin; op.act = kActSwish;
+        op.w = B.gemm_weight(n + "_expand_conv/kernel", cin, cexp, &sc);
+        op.bias = B.vec(sh);
+        CK(op.w && op.bias);
+        op.out_elems_per_clip = (size_t)h * w * cexp;
+        macs += (double)h * w * cin * cexp;
+        m->ops.push_back(op);
+      }
+      {
+        std::vector<float> sc, sh;
+        CK(B.bn(n + "_bn", cexp, &sc, &sh));
+        const int k = c.k;
+        const HostTensor* dk = B.get(n + "_dwconv/depthwise_kernel", (size_t)k * k * cexp);
+        const HostTensor* w1 = B.get(n + "_se_reduce/kernel", (size_t)cexp * se);
+        const HostTensor* b1 = B.get(n + "_se_reduce/bias", se);
+        const HostTensor* w2 = B.get(n + "_se_expand/kernel", (size_t)se * cexp);
+        const HostTensor* b2 = B.get(n + "_se_expand/bias", cexp);
+        CK(dk && w1 && b1 && w2 && b2);
+        std::vector<float> wd((size_t)k * k * cexp), w1t((size_t)se * cexp);
+        for (int t = 0; t < k * k; ++t)
+          for (int ch = 0; ch < cexp; ++ch) wd[(size_t)t * cexp + ch] = dk->data[(size_t)t * cexp + ch] * sc[ch];
+        for (int j = 0; j < se; ++j)
+          for (int ch = 0; ch < cexp; ++ch) w1t[(size_t)j * cexp + ch] = w1->data[(size_t)ch * se + j];
+        Op op;
+        op.kind = kOpDwse; op.name = n + "_se_excite"; op.in_buf = c.e != 1 ? 1 : 0; op.out_buf = 2;
+        DwseParams& P = op.dw;
+        P.H = h; P.W = w; P.C = cexp; P.K = k; P.S = stride; P.se = se;
+        if (stride == 2) {
+          P.pad_top = k / 2 - (1 - h % 2); P.pad_left = k / 2 - (1 - w % 2);
+          P.Ho = (h + P.pad_top + k / 2 - k) / 2 + 1; P.Wo = (w + P.pad_left + k / 2 - k) / 2 + 1;
+        } else {
+          P.pad_top = P.pad_left = k / 2; P.Ho = h; P.Wo = w;
+        }
+        P.w_dw = B.vec(wd); P.b_dw = B.vec(sh);
+        P.w_se1 = B.vec(w1t); P.b_se1 = B.vec(std::vector<float>(b1->data, b1->data + se));
+        P.w_se2 = B.vec(std::vector<float>(w2->data, w2->data + (size_t)se * cexp));
+        P.b_se2 = B.vec(std::vector<float>(b2->data, b2->data + cexp));
+        CK(P.w_dw && P.b_dw && P.w_se1 && P.b_se1 && P.w_se2 && P.b_se2);
+        op.dw_group = dwse_pick_group(P, m->max_smem);
+        if (op.dw_group < 1) { B.err = "depthwise layer " + n + " does not fit shared memory"; return fail(KWS_ERR_UNSUPPORTED); }
+        macs += (double)P.Ho * P.Wo * cexp * k * k + 2.0 * cexp * se;
+        h = P.Ho; w = P.Wo;
+        op.out_elems_per_clip = (size_t)h * w * cexp;
+        m->ops.push_back(op);
+      }
+      {
+        std::vector<float> sc, sh;
+        CK(B.bn(n + "_project_bn", cout, &sc, &sh));
+        Op op;
+        op.kind = kOpGemm; op.name = n + "_out"; op.in_buf = 2; op.out_buf = 0;
+        op.rows_per_clip = h * w; op.N = cout; op.K = cexp; op.act = kActNone;
+        op.res_buf = (stride == 1 && cin == cout) ? 0 : -1;
+        op.w = B.gemm_weight(n + "_project_conv/kernel", cexp, cout, &sc);
+        op.bias = B.vec(sh);
+        CK(op.w && op.bias);
+        op.out_elems_per_clip = (size_t)h * w * cout;
+        macs += (double)h * w * cexp * cout;
+        m->ops.push_back(op);
+      }
+    }
+  }
+  // ---- top conv + BN + swish + GAP (needs the 2x2 final map so the pool is a 4-row mean)
+  if (h * w != 4) { B.err = "top GAP epilogue expects a 2x2 final feature map"; return fail(KWS_ERR_UNSUPPORTED); }
+  {
+    std::vector<float> sc, sh;
+    CK(B.bn("top_bn", 1280, &sc, &sh));
+    Op op;
+    op.kind = kOpGemm; op.name = "top_gap"; op.in_buf = 0; op.out_buf = 1;
+    op.rows_per_clip = 4; op.N = 1280; op.K = 320; op.act = kActSwish; op.gap4 = 1;
+    op.w = B.gemm_weight("top_conv/kernel", 320, 1280, &sc);
+    op.bias = B.vec(sh);
+    CK(op.w && op.bias);
+    op.out_elems_per_clip = 1280;
+    macs += 4.0 * 320 * 1280;
+    m->ops.push_back(op);
+  }
+  // ---- dense tower: dense, dense_1, ... (relu ... relu, last = selu), cut at the last one present
+  {
+    int fan = 1280, idx = 0, in_buf = 1;
+    std::vector<std::string> names;
+    for (;; ++idx) {
+      const std::string nm = idx == 0 ? "dense" : "dense_" + std::to_string(idx);
+      if (wm.find(nm + "/kernel") == wm.end()) break;
+      names.push_back(nm);
+    }
+    if (names.empty()) { B.err = "no dense layers in the weight container"; return fail(KWS_ERR_ARG); }
+    for (size_t i = 0; i < names.size(); ++i) {
+      const HostTensor& kt = wm[names[i] + "/kernel"];
+      if (kt.dims.size() != 2 || (int)kt.dims[0] != fan) { B.err = "bad shape for " + names[i]; return fail(KWS_ERR_ARG); }
+      const int units = (int)kt.dims[1];
+      const HostTensor* bt = B.get(names[i] + "/bias", units);
+      CK(bt);
+      const bool last = i + 1 == names.size();
+      Op op;
+      op.kind = kOpGemm; op.name = names[i]; op.in_buf = in_buf; op.out_buf = last ? -1 : (in_buf == 1 ? 2 : 1);
+      op.rows_per_clip = 1; op.N = units; op.K = fan; op.act = last ? kActSelu : kActRelu; op.out_f32 = last ? 1 : 0;
+      op.w = B.gemm_weight(names[i] + "/kernel", fan, units, nullptr);
+      op.bias = B.vec(std::vector<float>(bt->data, bt->data + units));
+      CK(op.w && op.bias);
+      op.out_elems_per_clip = units;
+      macs += (double)fan * units;
+      m->ops.push_back(op);
+      in_buf = op.out_buf;
+      fan = units;
+    }
+    m->out_dim = fan;
+  }
+#undef CK
+  for (const Op& op : m->ops)
+    if (op.out_buf >= 0 && op.out_elems_per_clip > m->buf_elems[op.out_buf]) m->buf_elems[op.out_buf] = op.out_elems_per_clip;
+  for (int i = 0; i < 3; ++i) m->buf_elems[i] = round_up(m->buf_elems[i], 64);
+  m->flops_per_clip = 2.0 * macs;
+  *out = m;
+  return KWS_OK;
+}
+
+extern "C" void kws_embed_destroy(kws_embed_t* m) {
+  if (!m) return;
+  for (void* p : m->dev_allocs) cudaFree(p);
+  delete m;
+}
+
+extern "C" int kws_embed_info(const kws_embed_t* m, int* in_h, int* in_w, int* out_dim, int* n_ops, double* flops_per_clip) {
+  KWS_REQUIRE(m != nullptr, "kws_embed_info: NULL handle");
+  if (in_h) *in_h = m->H;
+  if (in_w) *in_w = m->W;
+  if (out_dim) *out_dim = m->out_dim;
+  if (n_ops) *n_ops = (int)m->ops.size();
+  if (flops_per_clip) *flops_per_clip = m->flops_per_clip;
+  return KWS_OK;
+}
+
+extern "C" int kws_embed_op_name(const kws_embed_t* m, int op, char* buf, size_t buf_bytes, int64_t* out_elems_per_clip) {
+  KWS_REQUIRE(m && op >= 0 && op < (int)m->ops.size(), "kws_embed_op_name: bad op index");
+  if (buf && buf_bytes) {
+    strncpy(buf, m->ops[op].name.c_str(), buf_bytes - 1);
+    buf[buf_bytes - 1] = 0;
+  }
+  if (out_elems_per_clip) *out_elems_per_clip = (int64_t)m->ops[op].out_elems_per_clip;
+  return KWS_OK;
+}
+
+extern "C" int kws_embed_set_chunk(kws_embed_t* m, int chunk) {
+  KWS_REQUIRE(m && chunk >= 1, "kws_embed_set_chunk: bad argument");
+  m->chunk = chunk;
+  return KWS_OK;
+}
+
+extern "C" size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch) {
+  if (!m || batch < 0) return 0;
+  const size_t c = (size_t)(batch < m->chunk ? batch : m->chunk);
+  return (m->buf_elems[0] + m->buf_elems[1] + m->buf_elems[2]) * 2 * c + 1024;
+}
+
+// tap_op >= 0: additionally copy the output of op `tap_op` (bf16 NHWC, or fp32 for the last op) to d_tap.
+extern "C" int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
+                                     size_t ws_bytes, int tap_op, void* d_tap, void* stream) {
+  KWS_REQUIRE(m != nullptr, "kws_embed_forward: NULL handle");
+  KWS_REQUIRE(batch >= 0, "kws_embed_forward: negative batch");
+  if (batch == 0) return KWS_OK;
+  KWS_REQUIRE(d_feats && d_emb && d_workspace, "kws_embed_forward: NULL device buffer");
+  KWS_REQUIRE(ws_bytes >= kws_embed_workspace_bytes(m, batch), "kws_embed_forward: workspace too small");
+  KWS_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "kws_embed_forward: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = batch < m->chunk ? batch : m->chunk;
+  __nv_bfloat16* bufs[3];
+  bufs[0] = static_cast<__nv_bfloat16*>(d_workspace);
+  bufs[1] = bufs[0] + m->buf_elems[0] * chunk;
+  bufs[2] = bufs[1] + m->buf_elems[1] * chunk;
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int nb = batch - b0 < chunk ? batch - b0 : chunk;
+    for (size_t oi = 0; oi < m->ops.size(); ++oi) {
+      const Op& op = m->ops[oi];
+      void* out_ptr = op.out_buf >= 0 ? (void*)bufs[op.out_buf] : (void*)(d_emb + (size_t)b0 * m->out_dim);
+      int rc = KWS_OK;
+      if (op.kind == kOpStem) {
+        rc = launch_stem(d_feats + (size_t)b0 * m->H * m->W, nb, op.stem, static_cast<__nv_bfloat16*>(out_ptr), m->sm_count, st);
+      } else if (op.kind == kOpDwse) {
+        rc = launch_dwse(bufs[op.in_buf], nb, op.dw, static_cast<__nv_bfloat16*>(out_ptr), op.dw_group, m->sm_count, st);
+      } else {
+        GemmShape sh;
+        sh.M = op.rows_per_clip * nb; sh.N = op.N; sh.K = op.K;
+        sh.m_tiles = (sh.M + kGemmBlockM - 1) / kGemmBlockM;
+        sh.block_n = pick_block_n(op.N, sh.m_tiles, m->sm_count);
+        sh.n_tiles = (op.N + sh.block_n - 1) / sh.block_n;
+        const int num_kb = (op.K + kGemmBlockK - 1) / kGemmBlockK;
+        int stages = (int)((200 * 1024) / (kGemmBlockM * kGemmBlockK * 2 + sh.block_n * kGemmBlockK * 2));
+        if (stages > kGemmMaxStages) stages = kGemmMaxStages;
+        if (stages > num_kb + 2) stages = num_kb + 2;
+        if (stages < 2) stages = 2;
+        sh.stages = stages;
+        CUtensorMap ta, tb;
+        rc = make_tmap_bf16_kmajor(&ta, bufs[op.in_buf], (uint64_t)sh.M, (uint64_t)op.K, kGemmBlockM);
+        if (rc == KWS_OK) rc = make_tmap_bf16_kmajor(&tb, op.w, (uint64_t)op.N, (uint64_t)op.K, (uint32_t)sh.block_n);
+        if (rc == KWS_OK) {
+          GemmEpilogue ep;
+          ep.bias = op.bias;
+          ep.residual = op.res_buf >= 0 ? bufs[op.res_buf] : nullptr;
+          ep.out = out_ptr; ep.ldo = op.N; ep.ldr = op.N;
+          ep.act = op.act; ep.out_f32 = op.out_f32; ep.gap4 = op.gap4;
+          rc = launch_gemm_tcgen05(ta, tb, sh, ep, m->sm_count, st);
+        }
+      }
+      if (rc != KWS_OK) return rc;
+      if ((int)oi == tap_op && d_tap) {
+        const size_t esz = op.out_f32 ? 4 : 2;
+        KWS_CUDA_CHECK(cudaMemcpyAsync(static_cast<uint8_t*>(d_tap) + (size_t)b0 * op.out_elems_per_clip * esz, out_ptr,
+                                       (size_t)nb * op.out_elems_per_clip * esz, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+  }
+  return KWS_OK;
+}
+
+extern "C" int kws_embed_forward(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
+                                 size_t ws_bytes, void* stream) {
+  return kws_embed_forward_tap(m, d_feats, batch, d_emb, d_workspace, ws_bytes, -1, nullptr, stream);
+}
+
+// Standalone tensor-core contraction with the fused epilogue (the "pointwise conv / dense" operator):
+// out[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual); A, W, residual bf16; out bf16 or fp32.
+extern "C" int kws_gemm_bf16(const void* d_a, const void* d_w, int M, int N, int K, const float* d_bias, int act,
+                             const void* d_residual, void* d_out, int out_f32, int gap4, int block_n, void* stream) {
+  KWS_REQUIRE(d_a && d_w && d_out && M >= 0 && N > 0 && K > 0, "kws_gemm_bf16: bad argument");
+  if (M == 0) return KWS_OK;
+  const int sm = device_sm_count();
+  KWS_REQUIRE(sm > 0, "kws_gemm_bf16: CUDA device required; there is no CPU fallback");
+  GemmShape sh;
+  sh.M = M; sh.N = N; sh.K = K;
+  sh.m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
+  sh.block_n = block_n > 0 ? block_n : pick_block_n(N, sh.m_tiles, sm);
+  sh.n_tiles = (N + sh.block_n - 1) / sh.block_n;
+  const int num_kb = (K + kGemmBlockK - 1) / kGemmBlockK;
+  int stages = (int)((200 * 1024) / (kGemmBlockM * kGemmBlockK * 2 + sh.block_n * kGemmBlockK * 2));
+  if (stages > kGemmMaxStages) stages = kGemmMaxStages;
+  if (stages > num_kb + 2) stages = num_kb + 2;
+  if (stages < 2) stages = 2;
+  sh.stages = stages;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_kmajor(&ta, d_a, (uint64_t)M, (uint64_t)K, kGemmBlockM);
+  if (rc != KWS_OK) return rc;
+  rc = make_tmap_bf16_kmajor(&tb, d_w, (uint64_t)N, (uint64_t)K, (uint32_t)sh.block_n);
+  if (rc != KWS_OK) return rc;
+  GemmEpilogue ep;
+  ep.bias = d_bias; ep.residual = static_cast<const __nv_bfloat16*>(d_residual);
+  ep.out = d_out; ep.ldo = N; ep.ldr = N; ep.act = act; ep.out_f32 = out_f32; ep.gap4 = gap4;
+  return launch_gemm_tcgen05(ta, tb, sh, ep, sm, (cudaStream_t)stream);
+}

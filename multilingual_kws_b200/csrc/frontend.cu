@@ -24,6 +24,7 @@
 #include "common.h"
 #include "frontend_core.cuh"
 #include "frontend_tables.h"
+#include "ptx.cuh"
 
 namespace kws {
 
@@ -39,33 +40,9 @@ static_assert(sizeof(FrontendTables) % 16 == 0, "tables are copied as uint4");
 constexpr int kClipThreads = 128;
 constexpr int kHalfWarpsPerCta = kClipThreads / kHalfWarp;
 
-// ---------------------------------------------------------------- PTX helpers (TMA bulk copy + mbarrier)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
+using ptx::mbar_expect_tx;
+using ptx::mbar_wait;
+using ptx::tma_bulk_g2s;
 
 // ---------------------------------------------------------------- one frame on one half-warp
 __device__ __forceinline__ void halfwarp_frame_mags(const uint32_t* frame_words, const FrontendTables& T,
@@ -117,7 +94,10 @@ frontend_clip_kernel(const int16_t* __restrict__ pcm, int n_samples, int n_frame
   const int16_t* clip_pcm = pcm + (size_t)clip * n_samples;
 
   if (use_tma) {
-    if (tid == 0) mbar_init(bar, 1);
+    if (tid == 0) {
+      ptx::mbar_init(bar, 1);
+      ptx::fence_barrier_init();
+    }
     __syncthreads();
     if (tid == 0) {
       mbar_expect_tx(bar, (uint32_t)stage_bytes);
@@ -201,6 +181,7 @@ constexpr int kTailGroup = 64;                       // threads per window
 constexpr int kTailWindows = kTailThreads / kTailGroup;
 
 // Window w (global index first_window + w) of row r starts at frame r*frames_per_row + wi*hop_frames.
+template <bool kSeq>
 __global__ void __launch_bounds__(kTailThreads)
 frontend_window_tail_kernel(const uint32_t* __restrict__ mags, long long first_window, long long n_windows,
                             long long windows_per_row, int frames_per_row, int hop_frames, int win_frames,
@@ -222,6 +203,20 @@ frontend_window_tail_kernel(const uint32_t* __restrict__ mags, long long first_w
     const long long row = gw / windows_per_row;
     const long long wi = gw - row * windows_per_row;
     const uint32_t* m = mags + (row * frames_per_row + wi * hop_frames) * num_channels;
+    if (kSeq) {   // windows too long to stage the estimates in smem: recurrence + tail per channel thread
+      if (valid && gt < num_channels) {
+        uint32_t est = 0;
+        const size_t obase = (size_t)w * total;
+        for (int t = 0; t < win_frames; ++t) {
+          const uint32_t sig = __ldg(m + t * num_channels + gt);
+          est = fe_noise_estimate(sig, est, gt, T);
+          const uint32_t v = fe_pointwise(sig, est, T);
+          if (out_f32) out_f32[obase + t * num_channels + gt] = (float)v * out_scale;
+          if (out_u16) out_u16[obase + t * num_channels + gt] = (uint16_t)v;
+        }
+      }
+      continue;
+    }
     if (valid && gt < num_channels) {
       uint32_t est = 0;
       for (int t = 0; t < win_frames; ++t) {
@@ -337,15 +332,16 @@ static int launch_split(kws_frontend* fe, const int16_t* d_pcm, long long rows, 
     }
   }
   if (n_windows > 0) {
-    const size_t smem = sizeof(FrontendTables) + (size_t)kTailWindows * win_frames * C * 4;
-    KWS_REQUIRE(smem <= (size_t)fe->max_smem_optin, "window of %d frames does not fit shared memory", win_frames);
-    KWS_CUDA_CHECK(cudaFuncSetAttribute(frontend_window_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = sizeof(FrontendTables) + (size_t)kTailWindows * win_frames * C * 4;
+    const bool seq = smem > (size_t)fe->max_smem_optin;
+    if (seq) smem = sizeof(FrontendTables);
+    auto kern = seq ? frontend_window_tail_kernel<true> : frontend_window_tail_kernel<false>;
+    KWS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (n_windows + kTailWindows - 1) / kTailWindows;
     const long long cap = (long long)fe->sm_count * 8;
     if (grid > cap) grid = cap;
-    frontend_window_tail_kernel<<<(unsigned)grid, kTailThreads, smem, st>>>(
-        d_mags, first_window, n_windows, windows_per_row, frames_per_row, hop_frames, win_frames, C, fe->dev, out_scale,
-        d_out_f32, d_out_u16);
+    kern<<<(unsigned)grid, kTailThreads, smem, st>>>(d_mags, first_window, n_windows, windows_per_row, frames_per_row,
+                                                    hop_frames, win_frames, C, fe->dev, out_scale, d_out_f32, d_out_u16);
     KWS_CUDA_CHECK(cudaGetLastError());
   }
   return KWS_OK;

@@ -1,0 +1,279 @@
+// gemm_tcgen05.cu — see gemm_tcgen05.cuh for the design.
+#include "gemm_tcgen05.cuh"
+
+#include <cuda_runtime.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace kws {
+
+namespace {
+
+constexpr uint32_t kABytes = kGemmBlockM * kGemmBlockK * 2;   // 16 KiB per stage
+
+struct SmemLayout {
+  uint32_t stage_bytes, bar_off, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int stages) {
+  SmemLayout L;
+  L.stage_bytes = kABytes + (uint32_t)block_n * kGemmBlockK * 2;
+  L.bar_off = L.stage_bytes * stages;
+  L.total = L.bar_off + 8 * (2 * kGemmMaxStages + 4) + 16;
+  return L;
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == kActSwish) return x / (1.0f + __expf(-x));
+  if (act == kActRelu) return fmaxf(x, 0.0f);
+  if (act == kActSelu) return x > 0.0f ? 1.0507009873554805f * x : 1.7580993408473766f * (__expf(x) - 1.0f);
+  return x;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmShape sh, const GemmEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const SmemLayout L = smem_layout(sh.block_n, sh.stages);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* empty_bar = full_bar + kGemmMaxStages;
+  uint64_t* tmem_full = empty_bar + kGemmMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int block_n = sh.block_n, stages = sh.stages;
+  const int num_kb = (sh.K + kGemmBlockK - 1) / kGemmBlockK;
+  const int k16_total = (sh.K + 15) / 16;
+  const int total_tiles = sh.m_tiles * sh.n_tiles;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)block_n) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&tmap_a);
+    ptx::tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        ptx::mbar_init(full_bar + s, 1);
+        ptx::mbar_init(empty_bar + s, 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        ptx::mbar_init(tmem_full + a, 1);
+        ptx::mbar_init(tmem_empty + a, 4);   // one arrive per epilogue warp
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_ptr_smem, tmem_cols);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_t = tile / sh.n_tiles, n_t = tile - m_t * sh.n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * L.stage_bytes;
+          ptx::mbar_expect_tx(full_bar + stage, L.stage_bytes);
+          ptx::tma_load_2d(&tmap_a, full_bar + stage, sa, kb * kGemmBlockK, m_t * kGemmBlockM);
+          ptx::tma_load_2d(&tmap_b, full_bar + stage, sa + kABytes, kb * kGemmBlockK, n_t * block_n);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16_f32(kGemmBlockM, block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * block_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar + stage, phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * L.stage_bytes);
+          const uint64_t a_desc = ptx::umma_desc_kmajor_sw128(sa);
+          const uint64_t b_desc = ptx::umma_desc_kmajor_sw128(sa + kABytes);
+          const int ksteps = min(4, k16_total - kb * 4);
+          for (int k = 0; k < ksteps; ++k)   // +32 B along K inside the 128 B swizzle atom = +2 in the (addr >> 4) field
+            ptx::tc_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          ptx::tc_commit(empty_bar + stage);              // smem slot free once these MMAs retire
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::tc_commit(tmem_full + acc);                  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_t = tile / sh.n_tiles, n_t = tile - m_t * sh.n_tiles;
+      ptx::mbar_wait(tmem_full + acc, acc_phase);
+      ptx::tc_fence_after();
+      const int row = m_t * kGemmBlockM + q * 32 + lane;
+      const bool row_ok = row < sh.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * block_n);
+      for (int c0 = 0; c0 < block_n; c0 += 16) {
+        const int n_base = n_t * block_n + c0;
+        if (n_base >= sh.N) break;                        // warp-uniform
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int n0 = n_base + 8 * g;
+          if (n0 >= sh.N) break;                          // N is a multiple of 8
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * g + j]);
+          if (ep.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
+          if (ep.residual && row_ok) {
+            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(ep.residual + (size_t)row * ep.ldr + n0));
+            const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[2 * j] += __uint_as_float(w[j] << 16);
+              v[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+            }
+          }
+          int orow = row;
+          bool store = row_ok;
+          if (ep.gap4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
+              v[j] += __shfl_xor_sync(0xffffffffu, v[j], 2);
+              v[j] *= 0.25f;
+            }
+            orow = row >> 2;
+            store = row_ok && ((lane & 3) == 0);
+          }
+          if (store) {
+            if (ep.out_f32) {
+              float* o = reinterpret_cast<float*>(ep.out) + (size_t)orow * ep.ldo + n0;
+              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)orow * ep.ldo + n0;
+              uint4 pk;
+              pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+              pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(o) = pk;
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tmem_empty + acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+size_t gemm_smem_bytes(int block_n, int stages) { return smem_layout(block_n, stages).total + 1024; }
+
+int make_tmap_bf16_kmajor(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is unavailable (CUDA driver too old or no device)");
+    return KWS_ERR_CUDA;
+  }
+  KWS_REQUIRE(cols % 8 == 0, "tensor map: inner dimension %llu must be a multiple of 8 bf16", (unsigned long long)cols);
+  KWS_REQUIRE(((uintptr_t)base & 15) == 0, "tensor map: base must be 16-byte aligned");
+  KWS_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box rows %u out of range", box_rows);
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kGemmBlockK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu box_rows %u)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    return KWS_ERR_CUDA;
+  }
+  return KWS_OK;
+}
+
+int launch_gemm_tcgen05(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmShape& shape,
+                        const GemmEpilogue& ep, int sm_count, cudaStream_t stream) {
+  KWS_REQUIRE(shape.block_n % 16 == 0 && shape.block_n >= 16 && shape.block_n <= 256, "gemm: bad block_n %d", shape.block_n);
+  KWS_REQUIRE(shape.stages >= 2 && shape.stages <= kGemmMaxStages, "gemm: bad stage count %d", shape.stages);
+  KWS_REQUIRE(shape.N % 8 == 0 && shape.K % 8 == 0, "gemm: N (%d) and K (%d) must be multiples of 8", shape.N, shape.K);
+  KWS_REQUIRE(!ep.gap4 || shape.M % 4 == 0, "gemm: gap4 epilogue needs M %% 4 == 0");
+  if (shape.M == 0) return KWS_OK;
+  const size_t smem = gemm_smem_bytes(shape.block_n, shape.stages);
+  static size_t configured = 0;
+  if (smem > configured) {
+    KWS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int tiles = shape.m_tiles * shape.n_tiles;
+  const int grid = tiles < sm_count ? tiles : sm_count;
+  gemm_tcgen05_kernel<<<grid, kGemmThreads, smem, stream>>>(tmap_a, tmap_b, shape, ep);
+  KWS_CUDA_CHECK(cudaGetLastError());
+  return KWS_OK;
+}
+
+}  // namespace kws

@@ -1,0 +1,153 @@
+"""Host-side model objects over the C ABI: the embedding extractor and (later) the few-shot model.
+
+``EmbeddingModel`` mirrors what the reference obtains from
+``distance_filtering.embedding_model()`` (multilingual_kws/embedding/distance_filtering.py:12-27):
+an object with ``.predict(specs[N,49,40(,1)]) -> [N,1024]`` and a ``.trainable`` attribute.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import struct
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import weights as W
+
+
+def pack_weights(w: Dict[str, np.ndarray]) -> bytes:
+    """Serialise Keras-named fp32 tensors into the 'KWSW0001' container kws_embed_create parses."""
+    parts = [b"KWSW0001", struct.pack("<I", len(w))]
+    for name, arr in w.items():
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        nb = name.encode("utf-8")
+        parts.append(struct.pack("<I", len(nb)))
+        parts.append(nb + b"\0" * ((4 - len(nb) % 4) % 4))
+        parts.append(struct.pack("<I", a.ndim))
+        parts.append(struct.pack(f"<{a.ndim}I", *a.shape) if a.ndim else b"")
+        parts.append(a.tobytes())
+    return b"".join(parts)
+
+
+class EmbeddingModel:
+    """EfficientNet-B0 embedding tower resident on the current CUDA device (inference mode, BN folded)."""
+
+    def __init__(self, weights: Dict[str, np.ndarray], chunk: Optional[int] = None):
+        self.weights = weights
+        self.trainable = False          # the reference sets embedding.trainable = False (distance_filtering.py:26)
+        self.name = "TransferLearnedModel"
+        blob = pack_weights(weights)
+        self._h = ctypes.c_void_p()
+        L = _lib.lib()
+        _lib.check(L.kws_embed_create(ctypes.byref(self._h), blob, len(blob)), "kws_embed_create")
+        h, w_, d, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        fl = ctypes.c_double()
+        _lib.check(L.kws_embed_info(self._h, ctypes.byref(h), ctypes.byref(w_), ctypes.byref(d), ctypes.byref(n),
+                                    ctypes.byref(fl)))
+        self.input_hw, self.output_dim, self.n_ops, self.flops_per_clip = (h.value, w_.value), d.value, n.value, fl.value
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._ws = None
+        if chunk is not None:
+            self.set_chunk(chunk)
+
+    @classmethod
+    def random(cls, seed: int = 0, **kw) -> "EmbeddingModel":
+        return cls(W.random_init(seed), **kw)
+
+    @classmethod
+    def load(cls, path: os.PathLike, **kw) -> "EmbeddingModel":
+        p = str(path)
+        if os.path.isdir(p):
+            p = os.path.join(p, "weights.npz")
+        return cls(W.load_npz(p), **kw)
+
+    def save(self, path: os.PathLike) -> None:
+        os.makedirs(str(path), exist_ok=True)
+        W.save_npz(os.path.join(str(path), "weights.npz"), self.weights)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().kws_embed_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def set_chunk(self, chunk: int) -> None:
+        _lib.check(_lib.lib().kws_embed_set_chunk(self._h, int(chunk)))
+        self._ws = None
+
+    def op_names(self):
+        L = _lib.lib()
+        out = []
+        for i in range(self.n_ops):
+            buf = ctypes.create_string_buffer(128)
+            n = ctypes.c_int64()
+            _lib.check(L.kws_embed_op_name(self._h, i, buf, 128, ctypes.byref(n)))
+            out.append((buf.value.decode(), int(n.value)))
+        return out
+
+    def _workspace(self, batch: int) -> torch.Tensor:
+        need = int(_lib.lib().kws_embed_workspace_bytes(self._h, batch))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def forward_device(self, feats: torch.Tensor, out: Optional[torch.Tensor] = None, tap_op: int = -1):
+        """feats: CUDA float32 [B,49,40] (contiguous) -> CUDA float32 [B, output_dim].  With tap_op >= 0 also
+        returns that op's output (bf16 [B, elems], fp32 for the last op)."""
+        if feats.dim() == 4 and feats.shape[-1] == 1:
+            feats = feats[..., 0]
+        if feats.dim() != 3 or tuple(feats.shape[1:]) != self.input_hw:
+            raise ValueError(f"expected [N,{self.input_hw[0]},{self.input_hw[1]}(,1)] features, got {tuple(feats.shape)}")
+        feats = feats.to(device=self.device, dtype=torch.float32).contiguous()
+        B = feats.shape[0]
+        if out is None:
+            out = torch.empty((B, self.output_dim), dtype=torch.float32, device=self.device)
+        ws = self._workspace(B)
+        tap = None
+        tap_ptr = None
+        if tap_op >= 0:
+            name, elems = self.op_names()[tap_op]
+            last = tap_op == self.n_ops - 1
+            tap = torch.empty((B, elems), dtype=torch.float32 if last else torch.bfloat16, device=self.device)
+            tap_ptr = tap.data_ptr()
+        if B:
+            _lib.check(_lib.lib().kws_embed_forward_tap(self._h, feats.data_ptr(), B, out.data_ptr(), ws.data_ptr(),
+                                                        ws.numel(), int(tap_op), tap_ptr, _lib.current_stream_ptr()),
+                       "kws_embed_forward")
+        return (out, tap) if tap_op >= 0 else out
+
+    def predict(self, specs, batch_size: int = 4096, verbose: int = 0) -> np.ndarray:
+        """Keras-style predict: host array [N,49,40] / [N,49,40,1] -> np.float32 [N, output_dim]."""
+        x = torch.as_tensor(np.asarray(specs, dtype=np.float32))
+        if x.dim() == 4 and x.shape[-1] == 1:
+            x = x[..., 0]
+        outs = []
+        for i in range(0, x.shape[0], batch_size):
+            xb = x[i:i + batch_size].pin_memory().to(self.device, non_blocking=True)
+            outs.append(self.forward_device(xb).cpu())
+        if not outs:
+            return np.zeros((0, self.output_dim), np.float32)
+        return torch.cat(outs).numpy()
+
+    __call__ = forward_device
+
+
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0,
+              residual: Optional[torch.Tensor] = None, out_f32: bool = False, gap4: bool = False,
+              block_n: int = 0) -> torch.Tensor:
+    """The tcgen05 pointwise/dense operator: act(a @ w.T + bias) (+ residual).  a [M,K], w [N,K] bf16 CUDA."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_cuda and w.is_cuda
+    a, w = a.contiguous(), w.contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M // 4 if gap4 else M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=a.device)
+    _lib.check(_lib.lib().kws_gemm_bf16(a.data_ptr(), w.data_ptr(), M, N, K, bias.data_ptr() if bias is not None else None,
+                                        int(act), residual.data_ptr() if residual is not None else None, out.data_ptr(),
+                                        int(out_f32), int(gap4), int(block_n), _lib.current_stream_ptr()), "kws_gemm_bf16")
+    return out

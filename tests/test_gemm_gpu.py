@@ -1,0 +1,70 @@
+"""tcgen05 GEMM + fused epilogue vs a plain torch fp32 reference of the same op (bf16 inputs, fp32 accumulate)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SELU_L, SELU_A = 1.0507009873554805, 1.6732632423543772
+
+
+def ref(a, w, bias, act, residual, gap4):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == 1:
+        y = y * torch.sigmoid(y)
+    elif act == 2:
+        y = torch.relu(y)
+    elif act == 3:
+        y = SELU_L * torch.where(y > 0, y, SELU_A * (torch.exp(y) - 1))
+    if residual is not None:
+        y = y + residual.float()
+    if gap4:
+        y = y.view(-1, 4, y.shape[1]).mean(1)
+    return y
+
+
+CASES = [
+    # M, N, K, act, residual, out_f32, gap4, block_n
+    (1000, 96, 16, 1, False, False, False, 0),        # block2a expand: single k16 step, K < 64 (TMA zero fill)
+    (128, 16, 32, 0, False, False, False, 0),         # block1a project
+    (520, 24, 144, 0, True, False, False, 0),         # block2b project + residual, N < block_n
+    (333, 40, 240, 0, True, False, False, 0),         # ragged M, N=40 -> block_n 48
+    (777, 144, 24, 1, False, False, False, 0),        # K=24: second k16 step half zero-filled
+    (2048, 1152, 192, 1, False, False, False, 0),     # block6 expand, multiple n tiles
+    (1024, 320, 1152, 0, False, False, False, 0),     # block7a project, 18 k-blocks
+    (4096, 1280, 320, 1, False, False, True, 0),      # top conv + swish + GAP(2x2)
+    (1024, 2048, 1280, 2, False, False, False, 0),    # dense
+    (512, 1024, 2048, 3, False, True, False, 0),      # dense_2: selu, fp32 out
+    (300, 2048, 2048, 2, False, False, False, 256),   # forced block_n 256 (512 TMEM columns)
+    (5, 96, 16, 1, False, False, False, 0),           # tiny M
+    (70000, 96, 16, 1, False, False, False, 0),       # many tiles per CTA: exercises ring + TMEM phase wrap
+]
+
+
+@pytest.mark.parametrize("M,N,K,act,res,f32,gap4,bn", CASES)
+def test_gemm_matches_torch(kws_lib, M, N, K, act, res, f32, gap4, bn):
+    from multilingual_kws_b200.model import gemm_bf16
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.2
+    residual = (torch.randn(M, N, device="cuda", generator=g)).bfloat16() if res else None
+    out = gemm_bf16(a, w, bias, act, residual, f32, gap4, bn)
+    torch.cuda.synchronize()
+    want = ref(a, w, bias, act, residual, gap4)
+    assert out.shape == want.shape
+    err = (out.float() - want).abs()
+    tol = 2e-3 + (0 if f32 else 1) * 2 ** -8 * want.abs()      # bf16 output rounding
+    assert bool((err <= tol + 1e-3 * want.abs()).all()), f"max err {err.max().item()} at {want.abs().max().item()}"
+
+
+def test_gemm_no_bias_identity(kws_lib):
+    from multilingual_kws_b200.model import gemm_bf16
+    K = 64
+    a = torch.randn(256, K, device="cuda").bfloat16()
+    w = torch.eye(K, device="cuda").bfloat16()
+    out = gemm_bf16(a, w, None, 0, None, True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, a.float())
