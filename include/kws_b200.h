@@ -76,9 +76,11 @@ int kws_frontend_stream(kws_frontend_t* fe, const int16_t* d_pcm, int64_t total_
  * multilingual_kws/train_multilingual_embedding.py:66-83 = Keras EfficientNetB0 + GAP + 3 Dense).
  * `blob` is the "KWSW0001" container of Keras-named fp32 tensors (multilingual_kws_b200/model.py
  * writes it).  BatchNorm is folded at create time (inference mode, as every reference forward outside
- * pre-training).  Activations are bf16 with fp32 accumulation; output is fp32 [batch, out_dim].
+ * pre-training).  Activations and tensor-core operands are 16-bit with fp32 accumulation: act_dtype 0 = IEEE
+ * fp16 (11-bit significand; default, what the parity tests run) or 1 = bf16 (wider range, 8-bit significand);
+ * output is fp32 [batch, out_dim].
  * ------------------------------------------------------------------------------------------- */
-int kws_embed_create(kws_embed_t** out, const void* blob, size_t bytes);
+int kws_embed_create(kws_embed_t** out, const void* blob, size_t bytes, int act_dtype /* 0 fp16, 1 bf16 */);
 void kws_embed_destroy(kws_embed_t* m);
 int kws_embed_info(const kws_embed_t* m, int* in_h, int* in_w, int* out_dim, int* n_ops, double* flops_per_clip);
 int kws_embed_op_name(const kws_embed_t* m, int op, char* buf, size_t buf_bytes, int64_t* out_elems_per_clip);
@@ -93,11 +95,34 @@ int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int batch, float
                           size_t ws_bytes, int tap_op, void* d_tap, void* stream);
 
 /* The pointwise-conv / dense operator on its own (tcgen05 GEMM + fused epilogue):
- * out[M,N] = act(A[M,K] x W[N,K]^T + bias[N]) (+ residual[M,N]); A, W, residual bf16 K-major; out bf16
+ * out[M,N] = act(A[M,K] x W[N,K]^T + bias[N]) (+ residual[M,N]); A, W, residual 16-bit K-major (dtype 0 fp16,
+ * 1 bf16); out same type
  * or fp32; act 0 none, 1 swish, 2 relu, 3 selu; gap4 averages aligned groups of 4 rows (out [M/4,N]);
  * block_n 0 = automatic.  N and K must be multiples of 8. */
-int kws_gemm_bf16(const void* d_a, const void* d_w, int M, int N, int K, const float* d_bias, int act,
-                  const void* d_residual, void* d_out, int out_f32, int gap4, int block_n, void* stream);
+int kws_gemm_h16(const void* d_a, const void* d_w, int M, int N, int K, const float* d_bias, int act,
+                 const void* d_residual, void* d_out, int out_f32, int gap4, int block_n, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Few-shot head — replaces what Keras runs for the trainable part of
+ *   Sequential[frozen embedding, Dense(18, tanh), Dense(3, softmax)] compiled with Adam(lr) and
+ *   SparseCategoricalCrossentropy  (multilingual_kws/embedding/transfer_learning.py:47-59) during
+ *   xfer.fit(...) / .predict(...) (:86-93, :196-198).
+ * Parameters are host fp32 arrays in Keras layouts: w1 [in_dim, hidden], b1 [hidden], w2 [hidden, classes],
+ * b2 [classes].  Flat gradient buffer layout (kws_head_flat_size() floats):
+ *   [dW1 | db1 | dW2 | db2 | loss_sum | n_correct | n_samples], gradients SUMMED over the local batch so one
+ *   all-reduce(sum) across ranks gives the global batch; kws_head_apply_adam divides by n_samples.
+ * ------------------------------------------------------------------------------------------- */
+int kws_head_create(kws_head_t** out, int in_dim, int hidden, int classes, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float beta1, float beta2, float eps);
+void kws_head_destroy(kws_head_t* h);
+size_t kws_head_flat_size(const kws_head_t* h);
+int kws_head_num_params(const kws_head_t* h);
+long long kws_head_step_count(const kws_head_t* h);
+int kws_head_forward(kws_head_t* h, const float* d_emb, int batch, float* d_probs, void* stream);
+int kws_head_grad(kws_head_t* h, const float* d_emb, const int32_t* d_labels, int batch, float* d_flat, void* stream);
+int kws_head_apply_adam(kws_head_t* h, const float* d_flat, float lr, void* stream);
+int kws_head_get_params(const kws_head_t* h, float* host_out);
+int kws_head_reset_optimizer(kws_head_t* h);
 
 #ifdef __cplusplus
 }

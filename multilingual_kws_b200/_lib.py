@@ -26,7 +26,7 @@ SIGNATURES = {
     "kws_frontend_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "kws_frontend_stream_num_windows": (c_int64, [c_void_p, c_int64, c_int, c_int]),
     "kws_frontend_stream_scratch_bytes": (c_size_t, [c_void_p, c_int64]),
-    "kws_embed_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_size_t]),
+    "kws_embed_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_size_t, c_int]),
     "kws_embed_destroy": (None, [c_void_p]),
     "kws_embed_info": (c_int, [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
                                ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double)]),
@@ -35,8 +35,19 @@ SIGNATURES = {
     "kws_embed_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "kws_embed_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "kws_embed_forward_tap": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
-    "kws_gemm_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
-                              c_int, c_void_p]),
+    "kws_gemm_h16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                             c_int, c_int, c_void_p]),
+    "kws_head_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_float, c_float, c_float]),
+    "kws_head_destroy": (None, [c_void_p]),
+    "kws_head_flat_size": (c_size_t, [c_void_p]),
+    "kws_head_num_params": (c_int, [c_void_p]),
+    "kws_head_step_count": (ctypes.c_longlong, [c_void_p]),
+    "kws_head_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "kws_head_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "kws_head_apply_adam": (c_int, [c_void_p, c_void_p, c_float, c_void_p]),
+    "kws_head_get_params": (c_int, [c_void_p, c_void_p]),
+    "kws_head_reset_optimizer": (c_int, [c_void_p]),
     "kws_frontend_stream": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_int64, c_float, c_void_p,
                                     c_void_p, c_int, c_void_p]),
 }

@@ -1,6 +1,6 @@
 // conv_kernels.cu — the non-GEMM kernels of the EfficientNet-B0 embedding tower (sm_100a):
 //   stem_conv_kernel   Rescaling(1/255) + ZeroPadding2D(correct_pad) + Conv3x3 s2 (1->32) + BN + swish,
-//                      fp32 log-mel features in, NHWC bf16 out.
+//                      fp32 log-mel features in, NHWC 16-bit (fp16 default, bf16 optional) out.
 //   dwse_kernel        one MBConv middle section per launch: depthwise kxk conv (TF SAME / correct_pad+VALID)
 //                      + folded BN + swish + squeeze-excite (global pool -> FC+swish -> FC+sigmoid -> scale),
 //                      whole clips staged in shared memory by TMA bulk copies; the pooled vector never
@@ -21,19 +21,13 @@ namespace {
 
 __device__ __forceinline__ float swish(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + __expf(-x)); }
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 // ---------------------------------------------------------------- stem
 constexpr int kStemThreads = 256;
 constexpr int kStemC = 32;
 
 __global__ void __launch_bounds__(kStemThreads)
-stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, __nv_bfloat16* __restrict__ out) {
+stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, uint16_t* __restrict__ out) {
   extern __shared__ __align__(128) uint8_t smem[];
   float* s_in = reinterpret_cast<float*>(smem);                     // [H*W]
   float* s_w = s_in + ((P.H * P.W + 3) & ~3);                        // [9][32]
@@ -69,10 +63,10 @@ stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, __nv_
         }
       }
       uint4 pk;
-      pk.x = pack_bf16x2(swish(acc[0]), swish(acc[1]));
-      pk.y = pack_bf16x2(swish(acc[2]), swish(acc[3]));
-      pk.z = pack_bf16x2(swish(acc[4]), swish(acc[5]));
-      pk.w = pack_bf16x2(swish(acc[6]), swish(acc[7]));
+      pk.x = ptx::pack_h2(swish(acc[0]), swish(acc[1]), P.bf16);
+      pk.y = ptx::pack_h2(swish(acc[2]), swish(acc[3]), P.bf16);
+      pk.z = ptx::pack_h2(swish(acc[4]), swish(acc[5]), P.bf16);
+      pk.w = ptx::pack_h2(swish(acc[6]), swish(acc[7]), P.bf16);
       *reinterpret_cast<uint4*>(out + ((size_t)clip * npix + p) * kStemC + g * 8) = pk;
     }
   }
@@ -97,7 +91,7 @@ __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
 
 template <int K, int S>
 __global__ void __launch_bounds__(kDwThreads)
-dwse_kernel(const __nv_bfloat16* __restrict__ x, int batch, int G, DwseParams P, __nv_bfloat16* __restrict__ y) {
+dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint16_t* __restrict__ y) {
   extern __shared__ __align__(128) uint8_t smem[];
   const DwSmem L = dw_smem(P, G);
   const uint32_t* s_in = reinterpret_cast<const uint32_t*>(smem);              // bf16x2 words, [G][H][W][C/2]
@@ -160,15 +154,16 @@ dwse_kernel(const __nv_bfloat16* __restrict__ x, int batch, int G, DwseParams P,
                 const int c = wo * S + kw - P.pad_left;
                 if (c < 0 || c >= P.W) continue;
                 const uint32_t v = in_g[(r * P.W + c) * C2];
-                a0 = fmaf(bf_lo(v), wreg[kh * K + kw].x, a0);
-                a1 = fmaf(bf_hi(v), wreg[kh * K + kw].y, a1);
+                const float2 xv = ptx::unpack_h2(v, P.bf16);
+                a0 = fmaf(xv.x, wreg[kh * K + kw].x, a0);
+                a1 = fmaf(xv.y, wreg[kh * K + kw].y, a1);
               }
             }
             a0 = swish(a0);
             a1 = swish(a1);
             sum0 += a0;
             sum1 += a1;
-            s_out[((size_t)g * npix + p) * C2 + cp] = pack_bf16x2(a0, a1);
+            s_out[((size_t)g * npix + p) * C2 + cp] = ptx::pack_h2(a0, a1, P.bf16);
           }
           if (PL == 1) {
             s_pool[g * C + 2 * cp] = sum0;
@@ -235,7 +230,8 @@ dwse_kernel(const __nv_bfloat16* __restrict__ x, int batch, int G, DwseParams P,
         const int cpair = i % C2;
         const uint32_t v = s_out[i];
         const float2 gate = *reinterpret_cast<const float2*>(&s_pool[g * C + 2 * cpair]);
-        dst[i] = pack_bf16x2(bf_lo(v) * gate.x, bf_hi(v) * gate.y);
+        const float2 xv = ptx::unpack_h2(v, P.bf16);
+        dst[i] = ptx::pack_h2(xv.x * gate.x, xv.y * gate.y, P.bf16);
       }
     }
     __syncthreads();
@@ -244,12 +240,12 @@ dwse_kernel(const __nv_bfloat16* __restrict__ x, int batch, int G, DwseParams P,
 
 }  // namespace
 
-int launch_stem(const float* d_feats, int batch, const StemParams& P, __nv_bfloat16* d_out, int sm_count,
+int launch_stem(const float* d_feats, int batch, const StemParams& P, void* d_out, int sm_count,
                 cudaStream_t st) {
   if (batch == 0) return KWS_OK;
   const size_t smem = (size_t)(((P.H * P.W + 3) & ~3) + 9 * kStemC + kStemC) * 4;
   const int grid = batch < sm_count * 4 ? batch : sm_count * 4;
-  stem_conv_kernel<<<grid, kStemThreads, smem, st>>>(d_feats, batch, P, d_out);
+  stem_conv_kernel<<<grid, kStemThreads, smem, st>>>(d_feats, batch, P, static_cast<uint16_t*>(d_out));
   KWS_CUDA_CHECK(cudaGetLastError());
   return KWS_OK;
 }
@@ -264,20 +260,20 @@ int dwse_pick_group(const DwseParams& P, int max_smem) {
   return 0;
 }
 
-int launch_dwse(const __nv_bfloat16* d_x, int batch, const DwseParams& P, __nv_bfloat16* d_y, int G, int sm_count,
+int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int G, int sm_count,
                 cudaStream_t st) {
   if (batch == 0) return KWS_OK;
   KWS_REQUIRE(G >= 1, "dwse: layer does not fit shared memory");
   KWS_REQUIRE(P.C % 8 == 0, "dwse: channels must be a multiple of 8");
   KWS_REQUIRE((P.K == 3 || P.K == 5) && (P.S == 1 || P.S == 2), "dwse: unsupported kernel %d / stride %d", P.K, P.S);
   const size_t smem = dw_smem(P, G).total;
-  void (*kern)(const __nv_bfloat16*, int, int, DwseParams, __nv_bfloat16*) =
+  void (*kern)(const uint16_t*, int, int, DwseParams, uint16_t*) =
       P.K == 3 ? (P.S == 1 ? dwse_kernel<3, 1> : dwse_kernel<3, 2>) : (P.S == 1 ? dwse_kernel<5, 1> : dwse_kernel<5, 2>);
   KWS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_groups = (batch + G - 1) / G;
   const int per_sm = smem <= 100 * 1024 ? 2 : 1;
   const int grid = n_groups < sm_count * per_sm ? n_groups : sm_count * per_sm;
-  kern<<<grid, kDwThreads, smem, st>>>(d_x, batch, G, P, d_y);
+  kern<<<grid, kDwThreads, smem, st>>>(static_cast<const uint16_t*>(d_x), batch, G, P, static_cast<uint16_t*>(d_y));
   KWS_CUDA_CHECK(cudaGetLastError());
   return KWS_OK;
 }

@@ -7,6 +7,7 @@ namespace kws {
 
 struct StemParams {
   int H, W, Ho, Wo, pad_top, pad_left;
+  int bf16;                   // output storage: 1 bf16, 0 fp16
   float in_scale, in_shift;   // Rescaling(1/255) + Normalization: x' = x*in_scale + in_shift
   const float* w;      // [9][32]  conv kernel * BN scale   (device)
   const float* bias;   // [32]     folded BN shift
@@ -14,6 +15,7 @@ struct StemParams {
 
 struct DwseParams {
   int H, W, C, Ho, Wo, K, S, pad_top, pad_left, se;
+  int bf16;            // activation storage: 1 bf16, 0 fp16
   const float* w_dw;   // [K*K][C]  depthwise kernel * BN scale
   const float* b_dw;   // [C]       folded BN shift
   const float* w_se1;  // [se][C]   se_reduce kernel (transposed)
@@ -22,9 +24,9 @@ struct DwseParams {
   const float* b_se2;  // [C]
 };
 
-int launch_stem(const float* d_feats, int batch, const StemParams& P, __nv_bfloat16* d_out, int sm_count, cudaStream_t st);
+int launch_stem(const float* d_feats, int batch, const StemParams& P, void* d_out, int sm_count, cudaStream_t st);
 int dwse_pick_group(const DwseParams& P, int max_smem);
-int launch_dwse(const __nv_bfloat16* d_x, int batch, const DwseParams& P, __nv_bfloat16* d_y, int G, int sm_count,
+int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int G, int sm_count,
                 cudaStream_t st);
 
 }  // namespace kws

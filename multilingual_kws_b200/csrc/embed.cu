@@ -13,6 +13,7 @@
 // Activations are NHWC bf16 in three ping-pong workspace buffers; the batch is walked in chunks so
 // one chunk's inter-layer activations stay resident in the 126 MB L2.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <string.h>
@@ -80,7 +81,7 @@ struct Op {
   int rows_per_clip = 0;       // GEMM: M = rows_per_clip * batch
   int N = 0, K = 0;
   int act = 0, gap4 = 0, out_f32 = 0;
-  const __nv_bfloat16* w = nullptr;   // GEMM weights [N][K]
+  const uint16_t* w = nullptr;        // GEMM weights [N][K], fp16 or bf16 bits
   const float* bias = nullptr;
   StemParams stem{};
   DwseParams dw{};
@@ -98,6 +99,7 @@ struct kws_embed {
   size_t buf_elems[3] = {0, 0, 0};     // per clip, bf16 elements
   int sm_count = 0, max_smem = 0;
   int chunk = 256;
+  int bf16 = 0;                        // 16-bit storage / tensor-core operand type: 0 fp16 (default), 1 bf16
   double flops_per_clip = 0;
 };
 
@@ -139,12 +141,18 @@ struct Builder {
     return true;
   }
   // 1x1 conv / dense kernel [K][N] (Keras) -> bf16 [N][K] with per-output scale
-  const __nv_bfloat16* gemm_weight(const std::string& name, int K, int N, const std::vector<float>* scale) {
+  const uint16_t* gemm_weight(const std::string& name, int K, int N, const std::vector<float>* scale) {
     const HostTensor* t = get(name, (size_t)K * N);
     if (!t) return nullptr;
-    std::vector<__nv_bfloat16> h((size_t)N * K);
+    std::vector<uint16_t> h((size_t)N * K);
     for (int n = 0; n < N; ++n)
-      for (int k = 0; k < K; ++k) h[(size_t)n * K + k] = __float2bfloat16(t->data[(size_t)k * N + n] * (scale ? (*scale)[n] : 1.0f));
+      for (int k = 0; k < K; ++k) {
+        const float v = t->data[(size_t)k * N + n] * (scale ? (*scale)[n] : 1.0f);
+        uint16_t bits;
+        if (m->bf16) { const __nv_bfloat16 b = __float2bfloat16(v); memcpy(&bits, &b, 2); }
+        else { const __half b = __float2half_rn(v); memcpy(&bits, &b, 2); }
+        h[(size_t)n * K + k] = bits;
+      }
     return upload(m, h, &cerr);
   }
   const float* vec(const std::vector<float>& v) { return upload(m, v, &cerr); }
@@ -167,9 +175,10 @@ int pick_block_n(int N, int m_tiles, int sm_count) {
 
 }  // namespace
 
-extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t bytes) {
+extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t bytes, int act_dtype) {
   KWS_REQUIRE(out && blob, "kws_embed_create: NULL argument");
   *out = nullptr;
+  KWS_REQUIRE(act_dtype == 0 || act_dtype == 1, "kws_embed_create: act_dtype must be 0 (fp16) or 1 (bf16)");
   WeightMap wm;
   std::string perr;
   if (!parse_blob(blob, bytes, &wm, &perr)) {
@@ -179,6 +188,7 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
   int dev = 0;
   kws_embed* m = new (std::nothrow) kws_embed();
   KWS_REQUIRE(m != nullptr, "out of host memory");
+  m->bf16 = act_dtype;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -224,7 +234,7 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
     op.stem.pad_top = 1 - (1 - h % 2); op.stem.pad_left = 1 - (1 - w % 2);
     op.stem.Ho = (h + op.stem.pad_top + 1 - 3) / 2 + 1;
     op.stem.Wo = (w + op.stem.pad_left + 1 - 3) / 2 + 1;
-    op.stem.in_scale = m->in_scale; op.stem.in_shift = m->in_shift;
+    op.stem.in_scale = m->in_scale; op.stem.in_shift = m->in_shift; op.stem.bf16 = m->bf16;
     op.stem.w = B.vec(wf); op.stem.bias = B.vec(sh);
     CK(op.stem.w && op.stem.bias);
     h = op.stem.Ho; w = op.stem.Wo;
@@ -272,7 +282,7 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
         Op op;
         op.kind = kOpDwse; op.name = n + "_se_excite"; op.in_buf = c.e != 1 ? 1 : 0; op.out_buf = 2;
         DwseParams& P = op.dw;
-        P.H = h; P.W = w; P.C = cexp; P.K = k; P.S = stride; P.se = se;
+        P.H = h; P.W = w; P.C = cexp; P.K = k; P.S = stride; P.se = se; P.bf16 = m->bf16;
         if (stride == 2) {
           P.pad_top = k / 2 - (1 - h % 2); P.pad_left = k / 2 - (1 - w % 2);
           P.Ho = (h + P.pad_top + k / 2 - k) / 2 + 1; P.Wo = (w + P.pad_left + k / 2 - k) / 2 + 1;
@@ -411,8 +421,8 @@ extern "C" int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int b
   KWS_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "kws_embed_forward: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int chunk = batch < m->chunk ? batch : m->chunk;
-  __nv_bfloat16* bufs[3];
-  bufs[0] = static_cast<__nv_bfloat16*>(d_workspace);
+  uint16_t* bufs[3];
+  bufs[0] = static_cast<uint16_t*>(d_workspace);
   bufs[1] = bufs[0] + m->buf_elems[0] * chunk;
   bufs[2] = bufs[1] + m->buf_elems[1] * chunk;
   for (int b0 = 0; b0 < batch; b0 += chunk) {
@@ -422,9 +432,9 @@ extern "C" int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int b
       void* out_ptr = op.out_buf >= 0 ? (void*)bufs[op.out_buf] : (void*)(d_emb + (size_t)b0 * m->out_dim);
       int rc = KWS_OK;
       if (op.kind == kOpStem) {
-        rc = launch_stem(d_feats + (size_t)b0 * m->H * m->W, nb, op.stem, static_cast<__nv_bfloat16*>(out_ptr), m->sm_count, st);
+        rc = launch_stem(d_feats + (size_t)b0 * m->H * m->W, nb, op.stem, out_ptr, m->sm_count, st);
       } else if (op.kind == kOpDwse) {
-        rc = launch_dwse(bufs[op.in_buf], nb, op.dw, static_cast<__nv_bfloat16*>(out_ptr), op.dw_group, m->sm_count, st);
+        rc = launch_dwse(bufs[op.in_buf], nb, op.dw, out_ptr, op.dw_group, m->sm_count, st);
       } else {
         GemmShape sh;
         sh.M = op.rows_per_clip * nb; sh.N = op.N; sh.K = op.K;
@@ -438,14 +448,14 @@ extern "C" int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int b
         if (stages < 2) stages = 2;
         sh.stages = stages;
         CUtensorMap ta, tb;
-        rc = make_tmap_bf16_kmajor(&ta, bufs[op.in_buf], (uint64_t)sh.M, (uint64_t)op.K, kGemmBlockM);
-        if (rc == KWS_OK) rc = make_tmap_bf16_kmajor(&tb, op.w, (uint64_t)op.N, (uint64_t)op.K, (uint32_t)sh.block_n);
+        rc = make_tmap_h16_kmajor(&ta, bufs[op.in_buf], (uint64_t)sh.M, (uint64_t)op.K, kGemmBlockM, m->bf16);
+        if (rc == KWS_OK) rc = make_tmap_h16_kmajor(&tb, op.w, (uint64_t)op.N, (uint64_t)op.K, (uint32_t)sh.block_n, m->bf16);
         if (rc == KWS_OK) {
           GemmEpilogue ep;
           ep.bias = op.bias;
           ep.residual = op.res_buf >= 0 ? bufs[op.res_buf] : nullptr;
           ep.out = out_ptr; ep.ldo = op.N; ep.ldr = op.N;
-          ep.act = op.act; ep.out_f32 = op.out_f32; ep.gap4 = op.gap4;
+          ep.act = op.act; ep.out_f32 = op.out_f32; ep.gap4 = op.gap4; ep.bf16 = m->bf16;
           rc = launch_gemm_tcgen05(ta, tb, sh, ep, m->sm_count, st);
         }
       }
@@ -466,13 +476,14 @@ extern "C" int kws_embed_forward(kws_embed_t* m, const float* d_feats, int batch
 }
 
 // Standalone tensor-core contraction with the fused epilogue (the "pointwise conv / dense" operator):
-// out[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual); A, W, residual bf16; out bf16 or fp32.
-extern "C" int kws_gemm_bf16(const void* d_a, const void* d_w, int M, int N, int K, const float* d_bias, int act,
-                             const void* d_residual, void* d_out, int out_f32, int gap4, int block_n, void* stream) {
-  KWS_REQUIRE(d_a && d_w && d_out && M >= 0 && N > 0 && K > 0, "kws_gemm_bf16: bad argument");
+// out[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual); A, W, residual fp16 (dtype 0) or bf16 (1); out same or fp32.
+extern "C" int kws_gemm_h16(const void* d_a, const void* d_w, int M, int N, int K, const float* d_bias, int act,
+                            const void* d_residual, void* d_out, int out_f32, int gap4, int block_n, int dtype,
+                            void* stream) {
+  KWS_REQUIRE(d_a && d_w && d_out && M >= 0 && N > 0 && K > 0 && (dtype == 0 || dtype == 1), "kws_gemm_h16: bad argument");
   if (M == 0) return KWS_OK;
   const int sm = device_sm_count();
-  KWS_REQUIRE(sm > 0, "kws_gemm_bf16: CUDA device required; there is no CPU fallback");
+  KWS_REQUIRE(sm > 0, "kws_gemm_h16: CUDA device required; there is no CPU fallback");
   GemmShape sh;
   sh.M = M; sh.N = N; sh.K = K;
   sh.m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
@@ -485,12 +496,12 @@ extern "C" int kws_gemm_bf16(const void* d_a, const void* d_w, int M, int N, int
   if (stages < 2) stages = 2;
   sh.stages = stages;
   CUtensorMap ta, tb;
-  int rc = make_tmap_bf16_kmajor(&ta, d_a, (uint64_t)M, (uint64_t)K, kGemmBlockM);
+  int rc = make_tmap_h16_kmajor(&ta, d_a, (uint64_t)M, (uint64_t)K, kGemmBlockM, dtype);
   if (rc != KWS_OK) return rc;
-  rc = make_tmap_bf16_kmajor(&tb, d_w, (uint64_t)N, (uint64_t)K, (uint32_t)sh.block_n);
+  rc = make_tmap_h16_kmajor(&tb, d_w, (uint64_t)N, (uint64_t)K, (uint32_t)sh.block_n, dtype);
   if (rc != KWS_OK) return rc;
   GemmEpilogue ep;
-  ep.bias = d_bias; ep.residual = static_cast<const __nv_bfloat16*>(d_residual);
-  ep.out = d_out; ep.ldo = N; ep.ldr = N; ep.act = act; ep.out_f32 = out_f32; ep.gap4 = gap4;
+  ep.bias = d_bias; ep.residual = d_residual;
+  ep.out = d_out; ep.ldo = N; ep.ldr = N; ep.act = act; ep.out_f32 = out_f32; ep.gap4 = gap4; ep.bf16 = dtype;
   return launch_gemm_tcgen05(ta, tb, sh, ep, sm, (cudaStream_t)stream);
 }

@@ -30,11 +30,6 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmShape sh, const GemmEpilogue ep) {
@@ -100,7 +95,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16_f32(kGemmBlockM, block_n);
+      const uint32_t idesc = ptx::umma_idesc_h16_f32(kGemmBlockM, block_n, ep.bf16 ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -161,12 +156,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
           if (ep.residual && row_ok) {
-            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(ep.residual + (size_t)row * ep.ldr + n0));
+            // plain (coherent) load: the residual may alias the output buffer (in-place skip connection)
+            const uint4 rr = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(ep.residual) + (size_t)row * ep.ldr + n0);
             const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              v[2 * j] += __uint_as_float(w[j] << 16);
-              v[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+              const float2 f = ptx::unpack_h2(w[j], ep.bf16);
+              v[2 * j] += f.x;
+              v[2 * j + 1] += f.y;
             }
           }
           int orow = row;
@@ -187,10 +184,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
               *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
             } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)orow * ep.ldo + n0;
+              uint16_t* o = reinterpret_cast<uint16_t*>(ep.out) + (size_t)orow * ep.ldo + n0;
               uint4 pk;
-              pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
-              pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+              pk.x = ptx::pack_h2(v[0], v[1], ep.bf16); pk.y = ptx::pack_h2(v[2], v[3], ep.bf16);
+              pk.z = ptx::pack_h2(v[4], v[5], ep.bf16); pk.w = ptx::pack_h2(v[6], v[7], ep.bf16);
               *reinterpret_cast<uint4*>(o) = pk;
             }
           }
@@ -232,20 +229,20 @@ EncodeTiledFn get_encode_fn() {
 
 size_t gemm_smem_bytes(int block_n, int stages) { return smem_layout(block_n, stages).total + 1024; }
 
-int make_tmap_bf16_kmajor(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+int make_tmap_h16_kmajor(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bf16) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is unavailable (CUDA driver too old or no device)");
     return KWS_ERR_CUDA;
   }
-  KWS_REQUIRE(cols % 8 == 0, "tensor map: inner dimension %llu must be a multiple of 8 bf16", (unsigned long long)cols);
+  KWS_REQUIRE(cols % 8 == 0, "tensor map: inner dimension %llu must be a multiple of 8 elements", (unsigned long long)cols);
   KWS_REQUIRE(((uintptr_t)base & 15) == 0, "tensor map: base must be 16-byte aligned");
   KWS_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box rows %u out of range", box_rows);
   const cuuint64_t gdim[2] = {cols, rows};
   const cuuint64_t gstride[1] = {cols * 2};
   const cuuint32_t box[2] = {(cuuint32_t)kGemmBlockK, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

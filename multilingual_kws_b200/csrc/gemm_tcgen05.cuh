@@ -1,10 +1,10 @@
-// gemm_tcgen05.cuh — persistent, warp-specialised bf16 GEMM on Blackwell tensor cores (tcgen05 + TMEM + TMA)
+// gemm_tcgen05.cuh — persistent, warp-specialised 16-bit (fp16 / bf16) GEMM on Blackwell tensor cores (tcgen05 + TMEM + TMA)
 // with a fused pointwise epilogue.  Used for every dense contraction of the embedding tower: the 1x1
 // (pointwise) convolutions of the MBConv stack, the top conv (+ global average pool) and the dense
 // tower.  Replaces the cuDNN/cuBLAS calls Keras makes for
 // reference multilingual_kws/train_multilingual_embedding.py:66-83 (model definition).
 //
-//   D[M,N] = epilogue( A[M,K] (bf16, K-major) x W[N,K]^T (bf16, K-major) )      fp32 accumulate in TMEM
+//   D[M,N] = epilogue( A[M,K] (fp16|bf16, K-major) x W[N,K]^T (same type, K-major) )      fp32 accumulate in TMEM
 //   epilogue: + bias[N] (folded BatchNorm), activation, + residual[M,N], optional 4-row mean (GAP of the
 //   2x2 top activation), store bf16 or fp32.
 //
@@ -28,12 +28,13 @@ enum GemmAct : int { kActNone = 0, kActSwish = 1, kActRelu = 2, kActSelu = 3 };
 
 struct GemmEpilogue {
   const float* bias;                 // [N] or nullptr
-  const __nv_bfloat16* residual;     // [M, ldr] or nullptr
+  const void* residual;              // 16-bit [M, ldr] or nullptr
   void* out;                         // bf16 or fp32, row pitch ldo elements
   int ldo, ldr;
   int act;                           // GemmAct
   int out_f32;                       // 1: store float
   int gap4;                          // 1: average each aligned group of 4 rows -> row m/4
+  int bf16;                          // storage/operand type of A, W, residual, 16-bit out: 1 bf16, 0 fp16
 };
 
 struct GemmShape {
@@ -48,7 +49,7 @@ int launch_gemm_tcgen05(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, co
                         const GemmEpilogue& ep, int sm_count, cudaStream_t stream);
 
 // Host: 2-D bf16 K-major tensor map, box = {64, box_rows}, 128B swizzle, zero OOB fill.
-int make_tmap_bf16_kmajor(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+int make_tmap_h16_kmajor(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bf16);
 
 size_t gemm_smem_bytes(int block_n, int stages);
 

@@ -108,10 +108,31 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   return ((uint64_t)hi << 32) | lo;
 }
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a format [7,10), b format [10,13),
 // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__device__ __forceinline__ uint32_t umma_idesc_bf16_f32(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// fmt: 0 = F16, 1 = BF16 (F16F32Format) for both A and B.
+__device__ __forceinline__ uint32_t umma_idesc_h16_f32(int m, int n, int fmt) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- 16-bit storage helpers: two values per 32-bit word; bf = 1 -> bfloat16, 0 -> IEEE half (saturating)
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi, int bf) {
+  uint32_t r;
+  if (bf) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  }
+  return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t w, int bf) {
+  if (bf) return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+  float2 r;
+  asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "r"(w));
+  return r;
 }
 
 }  // namespace ptx

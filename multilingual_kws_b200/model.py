@@ -35,14 +35,18 @@ def pack_weights(w: Dict[str, np.ndarray]) -> bytes:
 class EmbeddingModel:
     """EfficientNet-B0 embedding tower resident on the current CUDA device (inference mode, BN folded)."""
 
-    def __init__(self, weights: Dict[str, np.ndarray], chunk: Optional[int] = None):
+    def __init__(self, weights: Dict[str, np.ndarray], chunk: Optional[int] = None, dtype: str = "fp16"):
+        """dtype: 16-bit activation / tensor-core operand type, "fp16" (default, 11-bit significand) or "bf16"."""
+        if dtype not in ("fp16", "bf16"):
+            raise ValueError("dtype must be 'fp16' or 'bf16'")
+        self.dtype = dtype
         self.weights = weights
         self.trainable = False          # the reference sets embedding.trainable = False (distance_filtering.py:26)
         self.name = "TransferLearnedModel"
         blob = pack_weights(weights)
         self._h = ctypes.c_void_p()
         L = _lib.lib()
-        _lib.check(L.kws_embed_create(ctypes.byref(self._h), blob, len(blob)), "kws_embed_create")
+        _lib.check(L.kws_embed_create(ctypes.byref(self._h), blob, len(blob), 0 if dtype == "fp16" else 1), "kws_embed_create")
         h, w_, d, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         fl = ctypes.c_double()
         _lib.check(L.kws_embed_info(self._h, ctypes.byref(h), ctypes.byref(w_), ctypes.byref(d), ctypes.byref(n),
@@ -114,7 +118,8 @@ class EmbeddingModel:
         if tap_op >= 0:
             name, elems = self.op_names()[tap_op]
             last = tap_op == self.n_ops - 1
-            tap = torch.empty((B, elems), dtype=torch.float32 if last else torch.bfloat16, device=self.device)
+            tap = torch.empty((B, elems), dtype=torch.float32 if last else (torch.float16 if self.dtype == "fp16" else torch.bfloat16),
+                              device=self.device)
             tap_ptr = tap.data_ptr()
         if B:
             _lib.check(_lib.lib().kws_embed_forward_tap(self._h, feats.data_ptr(), B, out.data_ptr(), ws.data_ptr(),
@@ -138,16 +143,17 @@ class EmbeddingModel:
     __call__ = forward_device
 
 
-def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0,
-              residual: Optional[torch.Tensor] = None, out_f32: bool = False, gap4: bool = False,
-              block_n: int = 0) -> torch.Tensor:
-    """The tcgen05 pointwise/dense operator: act(a @ w.T + bias) (+ residual).  a [M,K], w [N,K] bf16 CUDA."""
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_cuda and w.is_cuda
+def gemm_h16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0,
+             residual: Optional[torch.Tensor] = None, out_f32: bool = False, gap4: bool = False,
+             block_n: int = 0) -> torch.Tensor:
+    """The tcgen05 pointwise/dense operator: act(a @ w.T + bias) (+ residual).  a [M,K], w [N,K] CUDA fp16 or bf16."""
+    assert a.dtype in (torch.float16, torch.bfloat16) and w.dtype == a.dtype and a.is_cuda and w.is_cuda
     a, w = a.contiguous(), w.contiguous()
     M, K = a.shape
     N = w.shape[0]
-    out = torch.empty((M // 4 if gap4 else M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=a.device)
-    _lib.check(_lib.lib().kws_gemm_bf16(a.data_ptr(), w.data_ptr(), M, N, K, bias.data_ptr() if bias is not None else None,
-                                        int(act), residual.data_ptr() if residual is not None else None, out.data_ptr(),
-                                        int(out_f32), int(gap4), int(block_n), _lib.current_stream_ptr()), "kws_gemm_bf16")
+    out = torch.empty((M // 4 if gap4 else M, N), dtype=torch.float32 if out_f32 else a.dtype, device=a.device)
+    _lib.check(_lib.lib().kws_gemm_h16(a.data_ptr(), w.data_ptr(), M, N, K, bias.data_ptr() if bias is not None else None,
+                                       int(act), residual.data_ptr() if residual is not None else None, out.data_ptr(),
+                                       int(out_f32), int(gap4), int(block_n), 0 if a.dtype == torch.float16 else 1,
+                                       _lib.current_stream_ptr()), "kws_gemm_h16")
     return out

@@ -98,10 +98,14 @@ def _trunc_normal(rng, shape, std):
     return (x * std).astype(np.float32)
 
 
-def random_init(seed: int = 0, dense_units=DENSE_UNITS, randomize_bn: bool = False) -> Dict[str, np.ndarray]:
+def random_init(seed: int = 0, dense_units=DENSE_UNITS, randomize_bn: bool = False,
+                residual_gamma_scale: float = 1.0) -> Dict[str, np.ndarray]:
     """Keras initialisers: conv kernels VarianceScaling(2.0, fan_out, truncated_normal); Dense
     glorot_uniform with zero bias (dense_2: lecun_normal); BN gamma 1, beta 0, mean 0, var 1.
-    randomize_bn=True draws non-trivial BN parameters/statistics (for parity tests of the folding)."""
+    randomize_bn=True draws non-trivial BN parameters/statistics (for parity tests of the folding).
+    residual_gamma_scale < 1 damps the project-BN of blocks that have a skip connection (the usual
+    'small residual branch' regime of trained residual nets; a BN network at pure random init amplifies
+    perturbations exponentially with depth and is not representative of a trained one)."""
     rng = np.random.default_rng(seed)
     w: Dict[str, np.ndarray] = {}
     last_dense = "dense" if len(dense_units) == 1 else f"dense_{len(dense_units) - 1}"
@@ -132,6 +136,11 @@ def random_init(seed: int = 0, dense_units=DENSE_UNITS, randomize_bn: bool = Fal
             w[name] = (rng.uniform(0.5, 1.5, shape) if randomize_bn else np.ones(shape)).astype(np.float32)
         else:
             raise AssertionError(name)
+    if residual_gamma_scale != 1.0:
+        for b in block_list():
+            if b["residual"]:
+                w[b["name"] + "_project_bn/gamma"] = w[b["name"] + "_project_bn/gamma"] * np.float32(residual_gamma_scale)
+                w[b["name"] + "_project_bn/beta"] = w[b["name"] + "_project_bn/beta"] * np.float32(residual_gamma_scale)
     if randomize_bn:   # SE biases are trainable too
         for name in w:
             if name.endswith("_se_reduce/bias") or name.endswith("_se_expand/bias"):

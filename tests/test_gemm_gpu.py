@@ -1,4 +1,4 @@
-"""tcgen05 GEMM + fused epilogue vs a plain torch fp32 reference of the same op (bf16 inputs, fp32 accumulate)."""
+"""tcgen05 GEMM + fused epilogue vs a plain torch fp32 reference of the same op (fp16 / bf16 inputs, fp32 accumulate)."""
 import numpy as np
 import pytest
 import torch
@@ -43,28 +43,30 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("M,N,K,act,res,f32,gap4,bn", CASES)
-def test_gemm_matches_torch(kws_lib, M, N, K, act, res, f32, gap4, bn):
-    from multilingual_kws_b200.model import gemm_bf16
+def test_gemm_matches_torch(kws_lib, M, N, K, act, res, f32, gap4, bn, dtype):
+    from multilingual_kws_b200.model import gemm_h16
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
-    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
-    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(dtype)
     bias = torch.randn(N, device="cuda", generator=g) * 0.2
-    residual = (torch.randn(M, N, device="cuda", generator=g)).bfloat16() if res else None
-    out = gemm_bf16(a, w, bias, act, residual, f32, gap4, bn)
+    residual = (torch.randn(M, N, device="cuda", generator=g)).to(dtype) if res else None
+    out = gemm_h16(a, w, bias, act, residual, f32, gap4, bn)
     torch.cuda.synchronize()
     want = ref(a, w, bias, act, residual, gap4)
     assert out.shape == want.shape
     err = (out.float() - want).abs()
-    tol = 2e-3 + (0 if f32 else 1) * 2 ** -8 * want.abs()      # bf16 output rounding
+    ulp = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    tol = 2e-3 + (0 if f32 else 1) * ulp * want.abs()          # 16-bit output rounding
     assert bool((err <= tol + 1e-3 * want.abs()).all()), f"max err {err.max().item()} at {want.abs().max().item()}"
 
 
 def test_gemm_no_bias_identity(kws_lib):
-    from multilingual_kws_b200.model import gemm_bf16
+    from multilingual_kws_b200.model import gemm_h16
     K = 64
-    a = torch.randn(256, K, device="cuda").bfloat16()
-    w = torch.eye(K, device="cuda").bfloat16()
-    out = gemm_bf16(a, w, None, 0, None, True)
+    a = torch.randn(256, K, device="cuda").half()
+    w = torch.eye(K, device="cuda").half()
+    out = gemm_h16(a, w, None, 0, None, True)
     torch.cuda.synchronize()
     assert torch.equal(out, a.float())
