@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the hot path (1 s / 16 kHz PCM -> log-mel frontend -> EfficientNet-B0 embedding) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N ...            the reference algorithm on the host CPU cores
+                                                           (oracle port: C frontend + torch-CPU fp32 network)
+
+A "step" is one pass of the hot path over one batch of synthetic clips (BASELINE.json configs[1]: batch = 1024
+clips per GPU; weak scaling, so N GPUs = config 4's 8192 at N = 8).  Rank 0 prints ONE JSON line.
+  value     utterances/s, inputs (int16 PCM) resident in HBM when the timed region starts, whole job over N GPUs
+  e2e       same metric through the public Python API with HOST buffers: pinned H2D of the PCM + frontend +
+            embedding + D2H of the embeddings inside the timed region
+  roofline  for the kernel with the largest share of the step (per-op CUDA events on the launch stream)
+  cpu_baseline  the oracle restatement of the reference algorithm timed on this box's host cores (rank 0, N = 1)
+  finetune  the 5-shot head fine-tune step (embedding forward + head fwd/bwd + one NCCL all-reduce + Adam)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "utterances/sec (1s@16kHz) embed-fwd"
+UNIT = "utterances/s"
+FRONTEND_BYTES_PER_CLIP = 39840          # 32 000 B int16 PCM in + 49*40*4 B features out
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's algorithm on the host CPU: C frontend oracle (all cores) + torch-CPU fp32 EfficientNet.
+    TensorFlow itself cannot be installed offline, so this is kind "port"."""
+    if rank != 0:
+        return
+    import torch
+    from multilingual_kws_b200 import weights as W
+    from multilingual_kws_b200.synthetic import synthetic_pcm
+    from oracle import effnet_oracle as EO
+    from oracle.frontend_oracle import FrontendOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = min(args.batch, args.ref_sample)
+    pcm = synthetic_pcm(B, cfg_id=2)
+    w = W.random_init(0, randomize_bn=True)
+    orc = FrontendOracle()
+
+    def step():
+        feats = orc.features(pcm, threads=cores)
+        with torch.no_grad():
+            return EO.forward(w, feats)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = B / dt
+    sample = f"{B} synthetic clips per step (of the {args.batch}-clip workload), frontend + embedding, {cores} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32 (CPU)", "data": "synthetic",
+        "config": {"workload": f"configs[1]: frontend + EfficientNet-B0 embedding forward, batch {args.batch} x 1 s clips",
+                   "sample_clips_per_step": B},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from multilingual_kws_b200 import build as kbuild
+    if rank == 0:
+        kbuild.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+    from multilingual_kws_b200 import weights as W
+    from multilingual_kws_b200.fewshot import FewShotModel, Head
+    from multilingual_kws_b200.frontend import FEATURE_SCALE, MicroFrontend
+    from multilingual_kws_b200.model import EmbeddingModel
+    from multilingual_kws_b200.synthetic import synthetic_pcm
+    from multilingual_kws_b200.embedding.transfer_learning import train_step
+
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    fe = MicroFrontend()
+    weights = W.random_init(0, randomize_bn=True, residual_gamma_scale=0.3)
+    emb_model = EmbeddingModel(weights, chunk=args.chunk, dtype=args.dtype)
+    base = synthetic_pcm(min(B, 256), cfg_id=2 + rank)
+    pcm_host = np.tile(base, (-(-B // base.shape[0]), 1))[:B]
+    pcm = torch.from_numpy(pcm_host).to(dev)
+    feats = torch.empty((B, 49, 40), dtype=torch.float32, device=dev)
+    emb = torch.empty((B, emb_model.output_dim), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def step():
+        fe.forward(pcm, out=feats)
+        emb_model.forward_device(feats, out=emb)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()                                                  # L2 flush between timed iterations
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            evs.append((s, e))
+        barrier()
+        wall = time.perf_counter() - t0
+        total_ms = sum(s.elapsed_time(e) for s, e in evs)
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms / steps, wall
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step, wall = timed(step, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- e2e: public API, host buffers (pinned), H2D + D2H inside the timed region
+    pcm_pinned = torch.from_numpy(pcm_host).pin_memory()
+    emb_pinned = torch.empty((B, emb_model.output_dim), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        d = pcm_pinned.to(dev, non_blocking=True)
+        f = fe.forward(d, out_scale=FEATURE_SCALE)
+        emb_pinned.copy_(emb_model.forward_device(f), non_blocking=True)
+
+    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    e2e_value = world * B / (ms_e2e * 1e-3)
+
+    # ---- fine-tune step (BASELINE config 3 shape): batch 512 / GPU, embedding fwd + head fwd/bwd + all-reduce + Adam
+    ft_B = 512
+    ft_model = FewShotModel(emb_model, Head.keras_init(emb_model.output_dim, 18, 3, seed=0))
+    ft_specs = feats[:ft_B].clone()
+    ft_labels = torch.randint(0, 3, (ft_B * world,), device=dev, dtype=torch.int32)
+
+    def step_ft():
+        # every rank owns its shard already (global batch = world * ft_B): emulate train_step's sharded path
+        e = emb_model.forward_device(ft_specs)
+        flat = ft_model.head.grad(e, ft_labels[rank * ft_B:(rank + 1) * ft_B])
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        ft_model.head.apply_adam(flat, 1e-3)
+
+    ms_ft, _ = timed(step_ft, args.steps, max(args.warmup, 3))
+
+    # ---- per-kernel shares (CUDA events around every launch, on the launch stream) -> roofline of the dominant kernel
+    peaks = load_peaks()
+    roof, shares = None, None
+    if rank == 0:
+        op_ms = np.zeros(emb_model.n_ops, np.float64)
+        fe_ms = 0.0
+        reps = max(3, min(args.steps, 10))
+        for _ in range(reps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fe.forward(pcm, out=feats); e.record()
+            _, ms = emb_model.forward_timed(feats)
+            op_ms += ms
+            fe_ms += s.elapsed_time(e)
+        op_ms /= reps
+        fe_ms /= reps
+        info = emb_model.op_info()
+        kinds = {0: "stem_conv_kernel", 1: "gemm_tcgen05_kernel", 2: "dwse_kernel"}
+        agg = {"frontend_clip_kernel": dict(ms=fe_ms, flops=0.0, bytes=FRONTEND_BYTES_PER_CLIP * B, launches=1)}
+        n_chunks = -(-B // args.chunk)
+        for (name, kind, fl, by, n, k, r), ms in zip(info, op_ms):
+            a = agg.setdefault(kinds[kind], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            a["ms"] += float(ms); a["flops"] += fl * B; a["bytes"] += by * B; a["launches"] += n_chunks
+        total = sum(a["ms"] for a in agg.values())
+        shares = {k: round(a["ms"] / total, 4) for k, a in agg.items()}
+        top = max(agg, key=lambda k: agg[k]["ms"])
+        a = agg[top]
+        if top == "gemm_tcgen05_kernel":
+            ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
+            peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+            roof = dict(kernel=top, bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                        launches_per_step=a["launches"], avg_launch_ms=a["ms"] / a["launches"],
+                        peak_source=peaks["source"] + ", sustained 16-bit dense GEMM",
+                        note="all launches of the kernel in one step: sum of algorithmic FLOPs / sum of launch durations")
+        else:
+            ach = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+            roof = dict(kernel=top, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
+                        traffic=None, launches_per_step=a["launches"], avg_launch_ms=a["ms"] / a["launches"],
+                        peak_source=peaks["source"],
+                        note="algorithmic activation bytes (read + write) of all launches of the kernel / sum of durations")
+        roof["per_kernel_ms"] = {k: round(v["ms"], 4) for k, v in agg.items()}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import effnet_oracle as EO
+        from oracle.frontend_oracle import FrontendOracle
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        nb = min(B, args.ref_sample)
+        orc = FrontendOracle()
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 2 or time.perf_counter() - t0 < 10.0:
+            f = orc.features(pcm_host[:nb], threads=cores)
+            with torch.no_grad():
+                ref_emb = EO.forward(weights, f)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": nb / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{reps} x {nb} synthetic clips (frontend C oracle on {cores} threads + torch-CPU fp32 network)"}
+        # parity spot-check against the oracle (checker only): same architecture/kernels, BN statistics calibrated
+        # by the oracle so activations have trained-like scale (the timed model uses un-calibrated random weights)
+        w2 = {k: v.copy() for k, v in weights.items()}
+        fs = f[:min(nb, 128)]
+        EO.forward(w2, fs, calibrate_bn=True)
+        with torch.no_grad():
+            want = EO.forward(w2, fs).numpy()
+        got = EmbeddingModel(w2, chunk=args.chunk, dtype=args.dtype).predict(fs)
+        cpu["parity_min_cosine_vs_oracle"] = float(EO.cosine(got, want).min())
+        feats_dev = fe.forward(pcm[:fs.shape[0]]).cpu().numpy()
+        cpu["parity_frontend_bit_exact"] = bool(np.array_equal(feats_dev, fs))
+
+    if rank == 0:
+        n_chunks = -(-B // args.chunk)
+        launches_per_step = 1 + emb_model.n_ops * n_chunks
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype + " storage / tensor-core operands, fp32 accumulate; frontend int16/int32/uint64 fixed point",
+            "data": "synthetic",
+            "config": {"workload": f"configs[1]: log-mel frontend + EfficientNet-B0 embedding forward, batch {B} x 1 s @ 16 kHz clips per GPU",
+                       "global_batch": B * world, "clip_samples": 16000, "parallelism": f"dp{world} (clips sharded, no collective)",
+                       "l2": "256 MiB buffer written between timed iterations (L2 flush)", "chunk": args.chunk,
+                       "weights": "random init (Keras initialisers, randomised BN), no checkpoint available offline"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 32000, "d2h_bytes_per_step": B * emb_model.output_dim * 4,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "clocks": clocks,
+            "roofline": roof,
+            "kernel_time_shares": shares,
+            "cpu_baseline": cpu,
+            "finetune": {"metric": "utterances/sec, 5-shot 3-way head fine-tune step (embedding fwd + head fwd/bwd + Adam)",
+                         "value": world * ft_B / (ms_ft * 1e-3), "unit": UNIT, "ms_per_step": ms_ft, "batch_per_gpu": ft_B,
+                         "collective": "one NCCL all-reduce(sum) of 18 510 fp32 per step" if world > 1 else "none (1 GPU)"},
+            "wall_s_timed_region": wall,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="clips per GPU per step")
+    ap.add_argument("--chunk", type=int, default=256, help="clips per pass through the layer list")
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--ref-sample", type=int, default=1024, help="clips per reference / cpu_baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun, one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -84,6 +84,9 @@ int kws_embed_create(kws_embed_t** out, const void* blob, size_t bytes, int act_
 void kws_embed_destroy(kws_embed_t* m);
 int kws_embed_info(const kws_embed_t* m, int* in_h, int* in_w, int* out_dim, int* n_ops, double* flops_per_clip);
 int kws_embed_op_name(const kws_embed_t* m, int op, char* buf, size_t buf_bytes, int64_t* out_elems_per_clip);
+/* op kind: 0 stem conv, 1 tcgen05 GEMM, 2 depthwise+SE; flops / algorithmic activation bytes per clip */
+int kws_embed_op_info(const kws_embed_t* m, int op, int* kind, double* flops_per_clip, double* bytes_per_clip,
+                      int* gemm_n, int* gemm_k, int* rows_per_clip);
 /* clips per pass through the layer list (keeps one chunk's activations L2-resident) */
 int kws_embed_set_chunk(kws_embed_t* m, int chunk);
 size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch);
@@ -93,6 +96,10 @@ int kws_embed_forward(kws_embed_t* m, const float* d_feats, int batch, float* d_
 /* same, additionally copying the output of op `tap_op` (bf16 NHWC; fp32 for the last op) to d_tap */
 int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
                           size_t ws_bytes, int tap_op, void* d_tap, void* stream);
+
+/* profiling: CUDA events around every op on `stream`; host_op_ms[n_ops] = device ms per op; synchronises */
+int kws_embed_forward_timed(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
+                            size_t ws_bytes, float* host_op_ms, void* stream);
 
 /* The pointwise-conv / dense operator on its own (tcgen05 GEMM + fused epilogue):
  * out[M,N] = act(A[M,K] x W[N,K]^T + bias[N]) (+ residual[M,N]); A, W, residual 16-bit K-major (dtype 0 fp16,

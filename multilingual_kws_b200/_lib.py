@@ -31,6 +31,10 @@ SIGNATURES = {
     "kws_embed_info": (c_int, [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
                                ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double)]),
     "kws_embed_op_name": (c_int, [c_void_p, c_int, ctypes.c_char_p, c_size_t, ctypes.POINTER(c_int64)]),
+    "kws_embed_op_info": (c_int, [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double),
+                                  ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+                                  ctypes.POINTER(c_int)]),
+    "kws_embed_forward_timed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "kws_embed_set_chunk": (c_int, [c_void_p, c_int]),
     "kws_embed_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "kws_embed_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

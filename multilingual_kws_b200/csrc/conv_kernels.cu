@@ -76,14 +76,18 @@ stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, uint1
 constexpr int kDwThreads = 256;
 
 struct DwSmem {
-  uint32_t in_bytes, out_off, pooled_off, s_off, bar_off, total;
+  uint32_t in_bytes, out_off, pooled_off, part_off, s_off, bar_off, total;
+  int PL;   // pixel lanes per channel pair
 };
 __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
   DwSmem L;
+  const int C2 = P.C >> 1;
+  L.PL = C2 >= kDwThreads ? 1 : kDwThreads / C2;
   L.in_bytes = (uint32_t)G * P.H * P.W * P.C * 2;
   L.out_off = (L.in_bytes + 127) & ~127u;
   L.pooled_off = L.out_off + (((uint32_t)G * P.Ho * P.Wo * P.C * 2 + 127) & ~127u);
-  L.s_off = L.pooled_off + (uint32_t)G * P.C * 4;
+  L.part_off = L.pooled_off + (uint32_t)G * P.C * 4;                       // [PL][G][C] partial channel sums
+  L.s_off = L.part_off + (L.PL > 1 ? (uint32_t)L.PL * G * P.C * 4 : 0u);
   L.bar_off = (L.s_off + (uint32_t)G * P.se * 4 + 15) & ~15u;
   L.total = L.bar_off + 16;
   return L;
@@ -97,6 +101,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
   const uint32_t* s_in = reinterpret_cast<const uint32_t*>(smem);              // bf16x2 words, [G][H][W][C/2]
   uint32_t* s_out = reinterpret_cast<uint32_t*>(smem + L.out_off);            // bf16x2, [G][Ho*Wo][C/2]
   float* s_pool = reinterpret_cast<float*>(smem + L.pooled_off);              // [G][C] sums, later gates
+  float* s_part = reinterpret_cast<float*>(smem + L.part_off);                // [PL][G][C] (deterministic pool reduce)
   float* s_se = reinterpret_cast<float*>(smem + L.s_off);                     // [G][se]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
 
@@ -112,7 +117,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
   __syncthreads();
 
   // thread -> (channel pair, pixel lane)
-  const int PL = C2 >= kDwThreads ? 1 : kDwThreads / C2;
+  const int PL = L.PL;
   const int cp0 = C2 >= kDwThreads ? tid : tid % C2;
   const int pl = C2 >= kDwThreads ? 0 : tid / C2;
   const bool active = pl < PL;
@@ -127,7 +132,6 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
       ptx::mbar_expect_tx(bar, bytes);
       ptx::tma_bulk_g2s(smem, x + (size_t)g0 * clip_words * 2, bytes, bar);
     }
-    for (int i = tid; i < gn * C; i += kDwThreads) s_pool[i] = 0.0f;
     ptx::mbar_wait(bar, parity);
     parity ^= 1;
     __syncthreads();
@@ -169,13 +173,21 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
             s_pool[g * C + 2 * cp] = sum0;
             s_pool[g * C + 2 * cp + 1] = sum1;
           } else {
-            atomicAdd(&s_pool[g * C + 2 * cp], sum0);
-            atomicAdd(&s_pool[g * C + 2 * cp + 1], sum1);
+            s_part[(pl * gn + g) * C + 2 * cp] = sum0;
+            s_part[(pl * gn + g) * C + 2 * cp + 1] = sum1;
           }
         }
       }
     }
     __syncthreads();
+    if (PL > 1) {                     // fixed-order sum over pixel lanes: results do not depend on scheduling
+      for (int i = tid; i < gn * C; i += kDwThreads) {
+        float a = 0.0f;
+        for (int q = 0; q < PL; ++q) a += s_part[q * gn * C + i];
+        s_pool[i] = a;
+      }
+      __syncthreads();
+    }
 
     // ---- SE reduce: s[g][j] = swish(b1[j] + mean_g . w1[j][:]); one warp per j, weights read once per group
     for (int j = warp; j < P.se; j += kDwThreads / 32) {

@@ -87,6 +87,8 @@ struct Op {
   DwseParams dw{};
   int dw_group = 1;
   size_t out_elems_per_clip = 0;
+  double flops_per_clip = 0;           // 2 * MACs
+  double bytes_per_clip = 0;           // algorithmic: activation read + write (weights excluded)
 };
 
 }  // namespace
@@ -364,6 +366,20 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
     m->out_dim = fan;
   }
 #undef CK
+  for (Op& op : m->ops) {
+    if (op.kind == kOpStem) {
+      op.flops_per_clip = 2.0 * op.stem.Ho * op.stem.Wo * 32 * 9;
+      op.bytes_per_clip = 4.0 * op.stem.H * op.stem.W + 2.0 * op.out_elems_per_clip;
+    } else if (op.kind == kOpDwse) {
+      const DwseParams& P = op.dw;
+      op.flops_per_clip = 2.0 * ((double)P.Ho * P.Wo * P.C * P.K * P.K + 2.0 * P.C * P.se);
+      op.bytes_per_clip = 2.0 * ((double)P.H * P.W * P.C + (double)P.Ho * P.Wo * P.C);
+    } else {
+      op.flops_per_clip = 2.0 * op.rows_per_clip * (double)op.N * op.K;
+      op.bytes_per_clip = 2.0 * op.rows_per_clip * op.K + (op.out_f32 ? 4.0 : 2.0) * op.out_elems_per_clip +
+                          (op.res_buf >= 0 ? 2.0 * op.out_elems_per_clip : 0.0);
+    }
+  }
   for (const Op& op : m->ops)
     if (op.out_buf >= 0 && op.out_elems_per_clip > m->buf_elems[op.out_buf]) m->buf_elems[op.out_buf] = op.out_elems_per_clip;
   for (int i = 0; i < 3; ++i) m->buf_elems[i] = round_up(m->buf_elems[i], 64);
@@ -398,6 +414,20 @@ extern "C" int kws_embed_op_name(const kws_embed_t* m, int op, char* buf, size_t
   return KWS_OK;
 }
 
+// kind: 0 stem, 1 gemm (tcgen05), 2 depthwise+SE.  flops / bytes are per clip (bytes: activations only).
+extern "C" int kws_embed_op_info(const kws_embed_t* m, int op, int* kind, double* flops_per_clip, double* bytes_per_clip,
+                                 int* gemm_n, int* gemm_k, int* rows_per_clip) {
+  KWS_REQUIRE(m && op >= 0 && op < (int)m->ops.size(), "kws_embed_op_info: bad op index");
+  const Op& o = m->ops[op];
+  if (kind) *kind = o.kind == kOpStem ? 0 : (o.kind == kOpGemm ? 1 : 2);
+  if (flops_per_clip) *flops_per_clip = o.flops_per_clip;
+  if (bytes_per_clip) *bytes_per_clip = o.bytes_per_clip;
+  if (gemm_n) *gemm_n = o.N;
+  if (gemm_k) *gemm_k = o.K;
+  if (rows_per_clip) *rows_per_clip = o.rows_per_clip;
+  return KWS_OK;
+}
+
 extern "C" int kws_embed_set_chunk(kws_embed_t* m, int chunk) {
   KWS_REQUIRE(m && chunk >= 1, "kws_embed_set_chunk: bad argument");
   m->chunk = chunk;
@@ -411,8 +441,8 @@ extern "C" size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch) {
 }
 
 // tap_op >= 0: additionally copy the output of op `tap_op` (bf16 NHWC, or fp32 for the last op) to d_tap.
-extern "C" int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
-                                     size_t ws_bytes, int tap_op, void* d_tap, void* stream) {
+static int embed_forward_impl(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
+                              size_t ws_bytes, int tap_op, void* d_tap, float* host_op_ms, void* stream) {
   KWS_REQUIRE(m != nullptr, "kws_embed_forward: NULL handle");
   KWS_REQUIRE(batch >= 0, "kws_embed_forward: negative batch");
   if (batch == 0) return KWS_OK;
@@ -425,8 +455,17 @@ extern "C" int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int b
   bufs[0] = static_cast<uint16_t*>(d_workspace);
   bufs[1] = bufs[0] + m->buf_elems[0] * chunk;
   bufs[2] = bufs[1] + m->buf_elems[1] * chunk;
+  std::vector<cudaEvent_t> evs;
+  if (host_op_ms) {
+    const size_t n_chunks = (size_t)(batch + chunk - 1) / chunk;
+    evs.resize(n_chunks * (m->ops.size() + 1));
+    for (auto& e : evs) KWS_CUDA_CHECK(cudaEventCreate(&e));
+    for (size_t i = 0; i < m->ops.size(); ++i) host_op_ms[i] = 0.f;
+  }
+  size_t ev_i = 0;
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int nb = batch - b0 < chunk ? batch - b0 : chunk;
+    if (host_op_ms) KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st));
     for (size_t oi = 0; oi < m->ops.size(); ++oi) {
       const Op& op = m->ops[oi];
       void* out_ptr = op.out_buf >= 0 ? (void*)bufs[op.out_buf] : (void*)(d_emb + (size_t)b0 * m->out_dim);
@@ -460,6 +499,7 @@ extern "C" int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int b
         }
       }
       if (rc != KWS_OK) return rc;
+      if (host_op_ms) KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st));
       if ((int)oi == tap_op && d_tap) {
         const size_t esz = op.out_f32 ? 4 : 2;
         KWS_CUDA_CHECK(cudaMemcpyAsync(static_cast<uint8_t*>(d_tap) + (size_t)b0 * op.out_elems_per_clip * esz, out_ptr,
@@ -467,12 +507,36 @@ extern "C" int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int b
       }
     }
   }
+  if (host_op_ms) {
+    KWS_CUDA_CHECK(cudaStreamSynchronize(st));
+    const size_t per = m->ops.size() + 1;
+    for (size_t c = 0; c * per < evs.size(); ++c)
+      for (size_t i = 0; i < m->ops.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evs[c * per + i], evs[c * per + i + 1]);
+        host_op_ms[i] += ms;
+      }
+    for (auto& e : evs) cudaEventDestroy(e);
+  }
   return KWS_OK;
+}
+
+extern "C" int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
+                                     size_t ws_bytes, int tap_op, void* d_tap, void* stream) {
+  return embed_forward_impl(m, d_feats, batch, d_emb, d_workspace, ws_bytes, tap_op, d_tap, nullptr, stream);
 }
 
 extern "C" int kws_embed_forward(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
                                  size_t ws_bytes, void* stream) {
-  return kws_embed_forward_tap(m, d_feats, batch, d_emb, d_workspace, ws_bytes, -1, nullptr, stream);
+  return embed_forward_impl(m, d_feats, batch, d_emb, d_workspace, ws_bytes, -1, nullptr, nullptr, stream);
+}
+
+// Profiling variant: CUDA events around every op on `stream`; host_op_ms[n_ops] receives the per-op device time
+// (summed over chunks).  Synchronises the stream.
+extern "C" int kws_embed_forward_timed(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
+                                       size_t ws_bytes, float* host_op_ms, void* stream) {
+  KWS_REQUIRE(host_op_ms != nullptr, "kws_embed_forward_timed: NULL timing buffer");
+  return embed_forward_impl(m, d_feats, batch, d_emb, d_workspace, ws_bytes, -1, nullptr, host_op_ms, stream);
 }
 
 // Standalone tensor-core contraction with the fused epilogue (the "pointwise conv / dense" operator):

@@ -1,0 +1,118 @@
+"""Streaming (sliding-window) inference, mirroring reference
+``multilingual_kws/embedding/batch_streaming_analysis.py:27-241``.
+
+The reference slides a 1 s window with a 20 ms stride over the wav and calls the CPU frontend once per window
+from a Python loop (:108-115) before one ``model.predict``.  Here the whole signal goes to the GPU once, the
+per-frame frontend work is computed once per 20 ms frame and shared by all windows (bit-identical, see
+kws_frontend_stream), and windows are embedded + classified in large batches.  Ground-truth accuracy bookkeeping
+(accuracy_utils / tpr_fpr in the reference) is out of scope; detections are returned in the same structure.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import input_data
+from .single_target_recognize_commands import detect_stream
+from ..frontend import FEATURE_SCALE, float_audio_to_int16_np
+
+
+@dataclass(frozen=True)
+class StreamFlags:
+    wav: os.PathLike
+    ground_truth: os.PathLike
+    target_keyword: str
+    detection_thresholds: List[float]
+    clip_duration_ms: int = 1000
+    clip_stride_ms: int = 20  # window_stride_ms in model_settings
+    average_window_duration_ms: int = 100
+    suppression_ms: int = 500
+    time_tolerance_ms: int = 750
+    minimum_count: int = 4
+    max_chunk_length_sec: int = 1200
+
+    def labels(self) -> List[str]:
+        return [input_data.SILENCE_LABEL, input_data.UNKNOWN_WORD_LABEL, self.target_keyword]
+
+
+@dataclass
+class StreamTarget:
+    target_lang: str
+    target_word: str
+    model_path: os.PathLike
+    stream_flags: List[StreamFlags]
+    destination_result_pkl: Optional[os.PathLike] = None
+    destination_result_inferences: Optional[os.PathLike] = None
+
+
+def stream_inferences(model, model_settings, audio: np.ndarray, sample_rate: int, clip_duration_ms: int,
+                      clip_stride_ms: int, window_batch: int = 8192) -> np.ndarray:
+    """softmax rows [W, n_labels] for every window offset in range(0, len - clip, stride)
+    (batch_streaming_analysis.py:66-117; the chunk branches there add up to the un-chunked result)."""
+    clip = int(clip_duration_ms * sample_rate / 1000)
+    stride = int(clip_stride_ms * sample_rate / 1000)
+    fe = input_data._frontend_for(model_settings)
+    pcm = torch.from_numpy(float_audio_to_int16_np(audio)).cuda()
+    W = fe.stream_num_windows(pcm.numel(), clip, stride)
+    n_labels = model.head.classes if hasattr(model, "head") else model.output_dim
+    if W <= 0:
+        return np.zeros((0, n_labels), np.float32)
+    st = fe.stream_prepare(pcm)
+    outs = []
+    for w0 in range(0, W, window_batch):
+        feats = st.windows(clip, stride, w0, min(window_batch, W - w0), FEATURE_SCALE)
+        outs.append(model.forward_device(feats).cpu())
+    return torch.cat(outs).numpy()
+
+
+def calculate_streaming_accuracy(model, model_settings, flag_list, existing_inferences=None):
+    assert len(set([f.wav for f in flag_list])) == 1, "can only process one wav"
+    assert len(set([f.clip_duration_ms for f in flag_list])) == 1, "cannot vary"
+    assert len(set([f.clip_stride_ms for f in flag_list])) == 1, "cannot vary"
+    f0 = flag_list[0]
+    with open(os.fspath(f0.wav), "rb") as fh:
+        audio, sample_rate = input_data.decode_wav(fh.read(), desired_channels=1)
+    audio = audio[:, 0]
+    clip_duration_samples = int(f0.clip_duration_ms * sample_rate / 1000)
+    clip_stride_samples = int(f0.clip_stride_ms * sample_rate / 1000)
+    audio_data_end = audio.shape[0] - clip_duration_samples
+    if existing_inferences is not None:
+        inferences = existing_inferences
+    else:
+        inferences = stream_inferences(model, model_settings, audio, sample_rate, f0.clip_duration_ms, f0.clip_stride_ms)
+    times = [int(o * 1000 / sample_rate) for o in range(0, audio_data_end, clip_stride_samples)]
+    results = []
+    for FLAGS in flag_list:
+        res_thresh = {}
+        for threshold in FLAGS.detection_thresholds:
+            found = detect_stream(inferences, times, FLAGS.labels(), FLAGS.average_window_duration_ms, threshold,
+                                  FLAGS.suppression_ms, FLAGS.minimum_count, target_id=2)
+            res_thresh[threshold] = ([[w, t] for w, t, _ in found], [[w, t, s] for w, t, s in found])
+        results.append((FLAGS, res_thresh))
+    return results, inferences
+
+
+def eval_stream_test(st: StreamTarget, live_model=None):
+    from ..fewshot import FewShotModel
+    model = live_model if live_model is not None else FewShotModel.load(st.model_path)
+    model_settings = input_data.standard_microspeech_model_settings(label_count=3)
+    if st.destination_result_pkl is not None and os.path.isfile(st.destination_result_pkl):
+        print("results already present", st.destination_result_pkl, flush=True)
+        return
+    loaded = None
+    if st.destination_result_inferences is not None and os.path.isfile(st.destination_result_inferences):
+        print("inferences already present", flush=True)
+        loaded = np.load(st.destination_result_inferences)
+    results = {}
+    results[st.target_word], inferences = calculate_streaming_accuracy(model, model_settings, st.stream_flags, loaded)
+    if st.destination_result_pkl is not None:
+        with open(st.destination_result_pkl, "wb") as fh:
+            pickle.dump(results, fh)
+    if loaded is None and st.destination_result_inferences is not None:
+        np.save(st.destination_result_inferences, inferences)
+    return results

@@ -1,0 +1,197 @@
+"""Drop-in mirror of reference ``multilingual_kws/embedding/transfer_learning.py`` on the B200 kernels.
+
+``transfer_learn`` keeps the reference signature and return triple (ref :14-123).  Per step it does what
+``xfer.fit`` does there with the embedding frozen (:43): frontend (fused kernel) -> embedding forward (tcgen05
+GEMMs + depthwise/SE kernels, BN in inference mode) -> head forward/backward (one kernel) -> Adam (one kernel).
+Under ``torch.distributed`` the global batch is sharded across ranks and the flat head gradient (+ loss/accuracy
+scalars) is summed with ONE NCCL all-reduce per step.
+"""
+from __future__ import annotations
+
+import csv
+import glob
+import logging
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import input_data
+from ..fewshot import FewShotModel, Head
+from ..model import EmbeddingModel
+
+AUTOTUNE = -1   # placeholder for tf.data.experimental.AUTOTUNE in the reference's call sites
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def train_step(model: FewShotModel, specs: torch.Tensor, labels: torch.Tensor, lr: float):
+    """One optimisation step on a GLOBAL batch (every rank passes the same batch; each computes its shard).
+    Returns (mean loss, accuracy) of the global batch as python floats."""
+    dist = _dist()
+    if dist is not None:
+        r, ws = dist.get_rank(), dist.get_world_size()
+        n = specs.shape[0]
+        lo, hi = n * r // ws, n * (r + 1) // ws
+        specs, labels = specs[lo:hi], labels[lo:hi]
+    flat = model.head._flat
+    if specs.shape[0] > 0:
+        emb = model.embedding.forward_device(specs)
+        model.head.grad(emb, labels, out=flat)
+    else:
+        flat.zero_()
+    if dist is not None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)      # head grads + loss/acc scalars, 74 KB, NCCL over NVLink
+    model.head.apply_adam(flat, lr)
+    n_p = model.head.n_params
+    stats = flat[n_p:n_p + 3].tolist()
+    cnt = max(stats[2], 1.0)
+    return stats[0] / cnt, stats[1] / cnt
+
+
+def evaluate(model: FewShotModel, ds) -> Dict[str, float]:
+    """Loss / accuracy over a (batched) dataset, forward only."""
+    loss_sum, correct, n = 0.0, 0, 0
+    for specs, labels in ds:
+        probs = model.forward_device(specs.cuda())
+        labels = labels.cuda()
+        p = probs.gather(1, labels.view(-1, 1).long()).clamp_min(1e-30)
+        loss_sum += float(-torch.log(p).sum())
+        correct += int((probs.argmax(1) == labels).sum())
+        n += labels.numel()
+    return dict(loss=loss_sum / max(n, 1), accuracy=correct / max(n, 1))
+
+
+def fit(model: FewShotModel, train_ds, validation_data, steps_per_epoch: int, epochs: int, lr: float,
+        csvlog_dest=None, verbose=1) -> Dict[str, List[float]]:
+    history = {"loss": [], "accuracy": [], "val_loss": [], "val_accuracy": []}
+    it = iter(train_ds)
+    writer = None
+    fh = None
+    if csvlog_dest is not None:
+        fh = open(csvlog_dest, "w", newline="")
+        writer = csv.writer(fh)
+        writer.writerow(["epoch", "accuracy", "loss", "val_accuracy", "val_loss"])   # Keras CSVLogger column order
+    for epoch in range(epochs):
+        loss_sum, acc_sum = 0.0, 0.0
+        for _ in range(steps_per_epoch):
+            specs, labels = next(it)
+            loss, acc = train_step(model, specs.cuda(), labels.cuda(), lr)
+            loss_sum += loss
+            acc_sum += acc
+        val = evaluate(model, validation_data)
+        history["loss"].append(loss_sum / steps_per_epoch)
+        history["accuracy"].append(acc_sum / steps_per_epoch)
+        history["val_loss"].append(val["loss"])
+        history["val_accuracy"].append(val["accuracy"])
+        if verbose:
+            print(f"Epoch {epoch + 1}/{epochs} - loss: {history['loss'][-1]:.4f} - accuracy: {history['accuracy'][-1]:.4f}"
+                  f" - val_loss: {val['loss']:.4f} - val_accuracy: {val['accuracy']:.4f}", flush=True)
+        if writer:
+            writer.writerow([epoch, history["accuracy"][-1], history["loss"][-1], val["accuracy"], val["loss"]])
+            fh.flush()
+    if fh:
+        fh.close()
+    return history
+
+
+def transfer_learn(
+    target,
+    train_files,
+    val_files,
+    unknown_files,
+    num_epochs,
+    num_batches,
+    batch_size,
+    primary_lr,
+    backprop_into_embedding,
+    embedding_lr,
+    model_settings: Dict,
+    base_model_path: os.PathLike,
+    base_model_output: str,
+    UNKNOWN_PERCENTAGE: float = 50.0,
+    bg_datadir: os.PathLike = "/home/mark/tinyspeech_harvard/speech_commands/_background_noise_/",
+    csvlog_dest: Optional[os.PathLike] = None,
+    verbose=1,
+):
+    """this only works for single-target models: see audio_dataset and CATEGORIES"""
+    embedding = EmbeddingModel.load(base_model_path, output_layer=base_model_output)
+    embedding.trainable = False
+
+    CATEGORIES = 3  # silence + unknown + target_keyword
+    xfer = FewShotModel(embedding, Head.keras_init(embedding.output_dim, 18, CATEGORIES))
+
+    audio_dataset = input_data.AudioDataset(
+        model_settings=model_settings,
+        commands=[target],
+        background_data_dir=bg_datadir,
+        unknown_files=unknown_files,
+        unknown_percentage=UNKNOWN_PERCENTAGE,
+        spec_aug_params=input_data.SpecAugParams(percentage=80),
+    )
+    init_train_ds = audio_dataset.init_single_target(AUTOTUNE, train_files, is_training=True)
+    init_val_ds = audio_dataset.init_single_target(AUTOTUNE, val_files, is_training=False)
+    train_ds = init_train_ds.shuffle(buffer_size=1000).repeat().batch(batch_size)
+    val_ds = init_val_ds.batch(batch_size)
+
+    # steps_per_epoch = batch_size * num_batches, as the reference passes it (transfer_learning.py:89)
+    history = fit(xfer, train_ds, val_ds, steps_per_epoch=batch_size * num_batches, epochs=num_epochs, lr=primary_lr,
+                  csvlog_dest=csvlog_dest, verbose=verbose)
+    if backprop_into_embedding:
+        # The reference's phase 2 un-freezes the whole nested embedding (transfer_learning.py:97-112).
+        # Backward through the EfficientNet stack is not built yet; fail loudly rather than silently skipping it.
+        raise NotImplementedError("backprop_into_embedding=True (full-embedding fine-tune) is not implemented")
+
+    va = history["val_accuracy"][-1]
+    name = f"xfer_epochs_{num_epochs}_bs_{batch_size}_nbs_{num_batches}_val_acc_{va:0.2f}_target_{target}"
+    details = dict(num_epochs=num_epochs, batch_size=batch_size, num_batches=num_batches, val_accuracy=va, target=target)
+    return name, xfer, details
+
+
+# ---- batch evaluators (reference :177-273): one frontend launch + one predict per call
+def _word_files(words_to_evaluate, data_dir, utterances_per_word):
+    files = []
+    for word in words_to_evaluate:
+        wavs = glob.glob(data_dir + word + "/*.wav")
+        if len(wavs) > utterances_per_word:
+            fs = np.random.choice(wavs, utterances_per_word, replace=False)
+        else:
+            print("using all wavs for ", word)
+            fs = wavs
+        files.extend(fs)
+    return files
+
+
+def _split_confidences(preds, target_id):
+    cols = np.argmax(preds, axis=1)
+    conf = preds[np.arange(preds.shape[0]), cols]
+    return dict(correct=conf[cols == target_id].tolist(), incorrect=conf[cols != target_id].tolist())
+
+
+def evaluate_files_single_target(files_to_evaluate: List[os.PathLike], target_id: int, model, model_settings: Dict):
+    specs = input_data.files2specs(model_settings, files_to_evaluate)
+    preds = model.predict(np.expand_dims(specs, -1))
+    return preds[:, target_id], preds
+
+
+def evaluate_files_multiclass(files_to_evaluate: List[os.PathLike], target_id: int, model, model_settings: Dict):
+    specs = input_data.files2specs(model_settings, files_to_evaluate)
+    return _split_confidences(model.predict(np.expand_dims(specs, -1)), target_id)
+
+
+def evaluate_fast_single_target(words_to_evaluate: List[str], target_id: int, data_dir: os.PathLike,
+                                utterances_per_word: int, model, model_settings: Dict):
+    return evaluate_files_single_target(_word_files(words_to_evaluate, data_dir, utterances_per_word), target_id, model,
+                                        model_settings)
+
+
+def evaluate_fast_multiclass(words_to_evaluate: List[str], target_id: int, data_dir: os.PathLike,
+                             utterances_per_word: int, model, model_settings: Dict):
+    return evaluate_files_multiclass(_word_files(words_to_evaluate, data_dir, utterances_per_word), target_id, model,
+                                     model_settings)

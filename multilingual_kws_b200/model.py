@@ -32,6 +32,16 @@ def pack_weights(w: Dict[str, np.ndarray]) -> bytes:
     return b"".join(parts)
 
 
+def cut_at(w: Dict[str, np.ndarray], output_layer: str) -> Dict[str, np.ndarray]:
+    """Drops every Dense layer after `output_layer` ("dense", "dense_1", ...) and the few-shot head entries."""
+    names = sorted({k.split("/")[0] for k in w if k.startswith("dense")}, key=lambda n: int(n.split("_")[1]) if "_" in n else 0)
+    if output_layer not in names:
+        raise ValueError(f"No such layer: {output_layer}. Existing dense layers are: {names}")
+    keep = set(names[:names.index(output_layer) + 1])
+    return {k: v for k, v in w.items()
+            if not k.startswith("fewshot_head/") and (not k.startswith("dense") or k.split("/")[0] in keep)}
+
+
 class EmbeddingModel:
     """EfficientNet-B0 embedding tower resident on the current CUDA device (inference mode, BN folded)."""
 
@@ -62,11 +72,15 @@ class EmbeddingModel:
         return cls(W.random_init(seed), **kw)
 
     @classmethod
-    def load(cls, path: os.PathLike, **kw) -> "EmbeddingModel":
+    def load(cls, path: os.PathLike, output_layer: str = "dense_2", **kw) -> "EmbeddingModel":
+        """Loads a saved weight container (directory with weights.npz, or the .npz itself) and cuts the dense tower
+        at `output_layer` (the reference cuts its classifier at "dense_2", transfer_learning.py:38-43)."""
         p = str(path)
         if os.path.isdir(p):
             p = os.path.join(p, "weights.npz")
-        return cls(W.load_npz(p), **kw)
+        if not os.path.isfile(p):
+            raise FileNotFoundError(f"no weight container at {p} (expected a directory holding weights.npz)")
+        return cls(cut_at(W.load_npz(p), output_layer), **kw)
 
     def save(self, path: os.PathLike) -> None:
         os.makedirs(str(path), exist_ok=True)
@@ -94,6 +108,30 @@ class EmbeddingModel:
             _lib.check(L.kws_embed_op_name(self._h, i, buf, 128, ctypes.byref(n)))
             out.append((buf.value.decode(), int(n.value)))
         return out
+
+    def op_info(self):
+        """[(name, kind, flops_per_clip, bytes_per_clip, N, K, rows_per_clip)] per op; kind 0 stem, 1 gemm, 2 dw+SE."""
+        L = _lib.lib()
+        out = []
+        for i, (name, _) in enumerate(self.op_names()):
+            kind, n, k, r = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            fl, by = ctypes.c_double(), ctypes.c_double()
+            _lib.check(L.kws_embed_op_info(self._h, i, ctypes.byref(kind), ctypes.byref(fl), ctypes.byref(by),
+                                           ctypes.byref(n), ctypes.byref(k), ctypes.byref(r)))
+            out.append((name, kind.value, fl.value, by.value, n.value, k.value, r.value))
+        return out
+
+    def forward_timed(self, feats: torch.Tensor):
+        """Profiling pass: returns (embeddings, per-op device milliseconds as a numpy array)."""
+        feats = feats.to(device=self.device, dtype=torch.float32).contiguous()
+        B = feats.shape[0]
+        out = torch.empty((B, self.output_dim), dtype=torch.float32, device=self.device)
+        ws = self._workspace(B)
+        ms = np.zeros(self.n_ops, np.float32)
+        _lib.check(_lib.lib().kws_embed_forward_timed(self._h, feats.data_ptr(), B, out.data_ptr(), ws.data_ptr(),
+                                                      ws.numel(), ms.ctypes.data, _lib.current_stream_ptr()),
+                   "kws_embed_forward_timed")
+        return out, ms
 
     def _workspace(self, batch: int) -> torch.Tensor:
         need = int(_lib.lib().kws_embed_workspace_bytes(self._h, batch))
