@@ -89,6 +89,12 @@ int kws_embed_op_info(const kws_embed_t* m, int op, int* kind, double* flops_per
                       int* gemm_n, int* gemm_k, int* rows_per_clip);
 /* clips per pass through the layer list (keeps one chunk's activations L2-resident) */
 int kws_embed_set_chunk(kws_embed_t* m, int chunk);
+/* clips per pass for the late (small-activation) layers; large values fill the SMs */
+int kws_embed_set_chunk_late(kws_embed_t* m, int chunk);
+/* 1 (default): capture the launch list of a forward pass into a CUDA graph per (buffers, batch) and replay it */
+int kws_embed_set_graph(kws_embed_t* m, int enable);
+/* kernel launches one forward pass of `batch` clips issues */
+int kws_embed_launches(const kws_embed_t* m, int batch);
 size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch);
 /* d_feats fp32 [batch, 49, 40] (the frontend's output) -> d_emb fp32 [batch, out_dim] */
 int kws_embed_forward(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,

@@ -35,6 +35,9 @@ SIGNATURES = {
                                   ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
                                   ctypes.POINTER(c_int)]),
     "kws_embed_forward_timed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "kws_embed_launches": (c_int, [c_void_p, c_int]),
+    "kws_embed_set_graph": (c_int, [c_void_p, c_int]),
+    "kws_embed_set_chunk_late": (c_int, [c_void_p, c_int]),
     "kws_embed_set_chunk": (c_int, [c_void_p, c_int]),
     "kws_embed_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "kws_embed_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

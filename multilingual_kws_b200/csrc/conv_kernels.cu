@@ -19,8 +19,8 @@ namespace kws {
 
 namespace {
 
-__device__ __forceinline__ float swish(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float swish(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------- stem
 constexpr int kStemThreads = 256;
@@ -146,8 +146,8 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
         for (int g = 0; g < gn; ++g) {
           const uint32_t* in_g = s_in + (size_t)g * clip_words + cp;
           float sum0 = 0.0f, sum1 = 0.0f;
+          int ho = pl / P.Wo, wo = pl - (pl / P.Wo) * P.Wo;
           for (int p = pl; p < npix; p += PL) {
-            const int ho = p / P.Wo, wo = p - ho * P.Wo;
             float a0 = bias.x, a1 = bias.y;
 #pragma unroll
             for (int kh = 0; kh < K; ++kh) {
@@ -168,6 +168,8 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
             sum0 += a0;
             sum1 += a1;
             s_out[((size_t)g * npix + p) * C2 + cp] = ptx::pack_h2(a0, a1, P.bf16);
+            wo += PL;
+            while (wo >= P.Wo) { wo -= P.Wo; ++ho; }
           }
           if (PL == 1) {
             s_pool[g * C + 2 * cp] = sum0;
@@ -196,6 +198,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
         float acc[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc[u] = 0.0f;
+#pragma unroll 4
         for (int c = lane; c < C; c += 32) {
           const float wv = __ldg(wrow + c);
 #pragma unroll
@@ -220,6 +223,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
         float acc[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc[u] = b2;
+#pragma unroll 8
         for (int j = 0; j < P.se; ++j) {
           const float wv = __ldg(P.w_se2 + (size_t)j * C + c);
 #pragma unroll
@@ -262,14 +266,16 @@ int launch_stem(const float* d_feats, int batch, const StemParams& P, void* d_ou
   return KWS_OK;
 }
 
-int dwse_pick_group(const DwseParams& P, int max_smem) {
-  // Largest G in {16,8,4,2,1} whose working set allows >= 2 CTAs per SM; else the largest that fits at all.
+int dwse_pick_group(const DwseParams& P, int max_smem, int batch, int sm_count) {
   const int cands[5] = {16, 8, 4, 2, 1};
-  for (int i = 0; i < 5; ++i)
-    if ((int)dw_smem(P, cands[i]).total <= 100 * 1024) return cands[i];
-  for (int i = 0; i < 5; ++i)
-    if ((int)dw_smem(P, cands[i]).total <= max_smem) return cands[i];
-  return 0;
+  int fit = 0;
+  for (int i = 0; i < 5 && !fit; ++i)
+    if ((int)dw_smem(P, cands[i]).total <= 100 * 1024) fit = cands[i];
+  for (int i = 0; i < 5 && !fit; ++i)
+    if ((int)dw_smem(P, cands[i]).total <= max_smem) fit = cands[i];
+  if (!fit) return 0;
+  while (fit > 1 && (batch + fit - 1) / fit < 2 * sm_count) fit >>= 1;   // keep every SM busy with >= 2 groups
+  return fit;
 }
 
 int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int G, int sm_count,

@@ -93,14 +93,26 @@ struct Op {
 
 }  // namespace
 
+struct GraphEntry {
+  const float* feats; float* emb; void* ws; int batch, chunk;
+  cudaGraphExec_t exec;
+};
+
 struct kws_embed {
+  std::vector<GraphEntry> graphs;      // captured forward passes, keyed by (buffers, batch, chunk)
+  int use_graph = 1;
   int H = 49, W = 40, out_dim = 0;
   float in_scale = 1.0f / 255.0f, in_shift = 0.0f;
   std::vector<Op> ops;
   std::vector<void*> dev_allocs;
-  size_t buf_elems[3] = {0, 0, 0};     // per clip, bf16 elements
+  // Two schedule segments.  "early" ops (stem .. the project conv of the block whose expanded map is the last big
+  // one) have up to 96 KB of activations per clip and are walked in small chunks so they stay L2-resident; "late"
+  // ops have <= 37 KB per clip and run over large chunks so GEMM tiles / depthwise groups fill the 148 SMs.
+  int split_op = 0;                    // first late op
+  size_t buf_elems[2][3] = {{0, 0, 0}, {0, 0, 0}};   // [segment][X, E, D] per clip, 16-bit elements
   int sm_count = 0, max_smem = 0;
-  int chunk = 256;
+  int chunk = 256;                     // early-segment clips per pass
+  int chunk_late = 2048;               // late-segment clips per pass
   int bf16 = 0;                        // 16-bit storage / tensor-core operand type: 0 fp16 (default), 1 bf16
   double flops_per_clip = 0;
 };
@@ -296,7 +308,7 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
         P.w_se2 = B.vec(std::vector<float>(w2->data, w2->data + (size_t)se * cexp));
         P.b_se2 = B.vec(std::vector<float>(b2->data, b2->data + cexp));
         CK(P.w_dw && P.b_dw && P.w_se1 && P.b_se1 && P.w_se2 && P.b_se2);
-        op.dw_group = dwse_pick_group(P, m->max_smem);
+        op.dw_group = dwse_pick_group(P, m->max_smem, 1 << 20, m->sm_count);
         if (op.dw_group < 1) { B.err = "depthwise layer " + n + " does not fit shared memory"; return fail(KWS_ERR_UNSUPPORTED); }
         macs += (double)P.Ho * P.Wo * cexp * k * k + 2.0 * cexp * se;
         h = P.Ho; w = P.Wo;
@@ -380,9 +392,21 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
                           (op.res_buf >= 0 ? 2.0 * op.out_elems_per_clip : 0.0);
     }
   }
-  for (const Op& op : m->ops)
-    if (op.out_buf >= 0 && op.out_elems_per_clip > m->buf_elems[op.out_buf]) m->buf_elems[op.out_buf] = op.out_elems_per_clip;
-  for (int i = 0; i < 3; ++i) m->buf_elems[i] = round_up(m->buf_elems[i], 64);
+  // split after the last op that produces or consumes more than 20 000 elements per clip
+  m->split_op = 0;
+  for (size_t i = 0; i < m->ops.size(); ++i)
+    if (m->ops[i].out_elems_per_clip > 20000) m->split_op = (int)i + 3 < (int)m->ops.size() ? (int)i + 3 : (int)m->ops.size();
+  // (expand op i -> dwse i+1 -> project i+2; the late segment starts at the next block)
+  for (size_t i = 0; i < m->ops.size(); ++i) {
+    const Op& op = m->ops[i];
+    const int seg = (int)i < m->split_op ? 0 : 1;
+    if (op.out_buf >= 0 && op.out_elems_per_clip > m->buf_elems[seg][op.out_buf]) m->buf_elems[seg][op.out_buf] = op.out_elems_per_clip;
+    // the hand-off tensor (output of the last early op) lives in the late X buffer
+    if ((int)i == m->split_op - 1 && op.out_buf == 0 && op.out_elems_per_clip > m->buf_elems[1][0])
+      m->buf_elems[1][0] = op.out_elems_per_clip;
+  }
+  for (int sgi = 0; sgi < 2; ++sgi)
+    for (int i = 0; i < 3; ++i) m->buf_elems[sgi][i] = round_up(m->buf_elems[sgi][i], 64);
   m->flops_per_clip = 2.0 * macs;
   *out = m;
   return KWS_OK;
@@ -390,6 +414,7 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
 
 extern "C" void kws_embed_destroy(kws_embed_t* m) {
   if (!m) return;
+  for (auto& g : m->graphs) cudaGraphExecDestroy(g.exec);
   for (void* p : m->dev_allocs) cudaFree(p);
   delete m;
 }
@@ -434,13 +459,41 @@ extern "C" int kws_embed_set_chunk(kws_embed_t* m, int chunk) {
   return KWS_OK;
 }
 
+extern "C" int kws_embed_set_chunk_late(kws_embed_t* m, int chunk) {
+  KWS_REQUIRE(m && chunk >= 1, "kws_embed_set_chunk_late: bad argument");
+  m->chunk_late = chunk;
+  return KWS_OK;
+}
+
+// Number of kernel launches one forward pass of `batch` clips issues (both schedule segments).
+extern "C" int kws_embed_launches(const kws_embed_t* m, int batch) {
+  if (!m || batch <= 0) return 0;
+  const int ce = batch < m->chunk ? batch : m->chunk, cl = batch < m->chunk_late ? batch : m->chunk_late;
+  const int n_ops = (int)m->ops.size();
+  return ((batch + ce - 1) / ce) * m->split_op + ((batch + cl - 1) / cl) * (n_ops - m->split_op);
+}
+
+extern "C" int kws_embed_set_graph(kws_embed_t* m, int enable) {
+  KWS_REQUIRE(m != nullptr, "kws_embed_set_graph: NULL handle");
+  m->use_graph = enable ? 1 : 0;
+  return KWS_OK;
+}
+
 extern "C" size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch) {
   if (!m || batch < 0) return 0;
-  const size_t c = (size_t)(batch < m->chunk ? batch : m->chunk);
-  return (m->buf_elems[0] + m->buf_elems[1] + m->buf_elems[2]) * 2 * c + 1024;
+  const size_t ce = (size_t)(batch < m->chunk ? batch : m->chunk);
+  const size_t cl = (size_t)(batch < m->chunk_late ? batch : m->chunk_late);
+  const size_t early = (m->buf_elems[0][0] + m->buf_elems[0][1] + m->buf_elems[0][2]) * ce;
+  const size_t late = m->buf_elems[1][0] * (size_t)batch + (m->buf_elems[1][1] + m->buf_elems[1][2]) * cl;
+  return (early + late) * 2 + 2048;
 }
 
 // tap_op >= 0: additionally copy the output of op `tap_op` (bf16 NHWC, or fp32 for the last op) to d_tap.
+static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace, int tap_op,
+                   void* d_tap, float* host_op_ms, cudaStream_t st);
+
+// The launch list of one forward pass is fixed for given buffers / batch, so it is captured once into a CUDA
+// graph (35 tensor-map encodes + ~55 launches per chunk collapse into one cudaGraphLaunch) and replayed.
 static int embed_forward_impl(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
                               size_t ws_bytes, int tap_op, void* d_tap, float* host_op_ms, void* stream) {
   KWS_REQUIRE(m != nullptr, "kws_embed_forward: NULL handle");
@@ -450,71 +503,129 @@ static int embed_forward_impl(kws_embed_t* m, const float* d_feats, int batch, f
   KWS_REQUIRE(ws_bytes >= kws_embed_workspace_bytes(m, batch), "kws_embed_forward: workspace too small");
   KWS_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "kws_embed_forward: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const int chunk = batch < m->chunk ? batch : m->chunk;
-  uint16_t* bufs[3];
-  bufs[0] = static_cast<uint16_t*>(d_workspace);
-  bufs[1] = bufs[0] + m->buf_elems[0] * chunk;
-  bufs[2] = bufs[1] + m->buf_elems[1] * chunk;
-  std::vector<cudaEvent_t> evs;
-  if (host_op_ms) {
-    const size_t n_chunks = (size_t)(batch + chunk - 1) / chunk;
-    evs.resize(n_chunks * (m->ops.size() + 1));
-    for (auto& e : evs) KWS_CUDA_CHECK(cudaEventCreate(&e));
-    for (size_t i = 0; i < m->ops.size(); ++i) host_op_ms[i] = 0.f;
-  }
-  size_t ev_i = 0;
-  for (int b0 = 0; b0 < batch; b0 += chunk) {
-    const int nb = batch - b0 < chunk ? batch - b0 : chunk;
-    if (host_op_ms) KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st));
-    for (size_t oi = 0; oi < m->ops.size(); ++oi) {
-      const Op& op = m->ops[oi];
-      void* out_ptr = op.out_buf >= 0 ? (void*)bufs[op.out_buf] : (void*)(d_emb + (size_t)b0 * m->out_dim);
-      int rc = KWS_OK;
-      if (op.kind == kOpStem) {
-        rc = launch_stem(d_feats + (size_t)b0 * m->H * m->W, nb, op.stem, out_ptr, m->sm_count, st);
-      } else if (op.kind == kOpDwse) {
-        rc = launch_dwse(bufs[op.in_buf], nb, op.dw, out_ptr, op.dw_group, m->sm_count, st);
-      } else {
-        GemmShape sh;
-        sh.M = op.rows_per_clip * nb; sh.N = op.N; sh.K = op.K;
-        sh.m_tiles = (sh.M + kGemmBlockM - 1) / kGemmBlockM;
-        sh.block_n = pick_block_n(op.N, sh.m_tiles, m->sm_count);
-        sh.n_tiles = (op.N + sh.block_n - 1) / sh.block_n;
-        const int num_kb = (op.K + kGemmBlockK - 1) / kGemmBlockK;
-        int stages = (int)((200 * 1024) / (kGemmBlockM * kGemmBlockK * 2 + sh.block_n * kGemmBlockK * 2));
-        if (stages > kGemmMaxStages) stages = kGemmMaxStages;
-        if (stages > num_kb + 2) stages = num_kb + 2;
-        if (stages < 2) stages = 2;
-        sh.stages = stages;
-        CUtensorMap ta, tb;
-        rc = make_tmap_h16_kmajor(&ta, bufs[op.in_buf], (uint64_t)sh.M, (uint64_t)op.K, kGemmBlockM, m->bf16);
-        if (rc == KWS_OK) rc = make_tmap_h16_kmajor(&tb, op.w, (uint64_t)op.N, (uint64_t)op.K, (uint32_t)sh.block_n, m->bf16);
-        if (rc == KWS_OK) {
-          GemmEpilogue ep;
-          ep.bias = op.bias;
-          ep.residual = op.res_buf >= 0 ? bufs[op.res_buf] : nullptr;
-          ep.out = out_ptr; ep.ldo = op.N; ep.ldr = op.N;
-          ep.act = op.act; ep.out_f32 = op.out_f32; ep.gap4 = op.gap4; ep.bf16 = m->bf16;
-          rc = launch_gemm_tcgen05(ta, tb, sh, ep, m->sm_count, st);
-        }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (m->use_graph && tap_op < 0 && !host_op_ms && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
+      cap == cudaStreamCaptureStatusNone) {
+    for (auto& g : m->graphs)
+      if (g.feats == d_feats && g.emb == d_emb && g.ws == d_workspace && g.batch == batch &&
+          g.chunk == m->chunk * 100003 + m->chunk_late) {
+        KWS_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+        return KWS_OK;
       }
-      if (rc != KWS_OK) return rc;
-      if (host_op_ms) KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st));
-      if ((int)oi == tap_op && d_tap) {
-        const size_t esz = op.out_f32 ? 4 : 2;
-        KWS_CUDA_CHECK(cudaMemcpyAsync(static_cast<uint8_t*>(d_tap) + (size_t)b0 * op.out_elems_per_clip * esz, out_ptr,
-                                       (size_t)nb * op.out_elems_per_clip * esz, cudaMemcpyDeviceToDevice, st));
+    KWS_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_ops(m, d_feats, batch, d_emb, d_workspace, -1, nullptr, nullptr, st);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != KWS_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    KWS_CUDA_CHECK(ce);
+    GraphEntry e{d_feats, d_emb, d_workspace, batch, m->chunk * 100003 + m->chunk_late, nullptr};
+    const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    KWS_CUDA_CHECK(ie);
+    if (m->graphs.size() >= 8) {
+      cudaGraphExecDestroy(m->graphs.front().exec);
+      m->graphs.erase(m->graphs.begin());
+    }
+    m->graphs.push_back(e);
+    KWS_CUDA_CHECK(cudaGraphLaunch(e.exec, st));
+    return KWS_OK;
+  }
+  return run_ops(m, d_feats, batch, d_emb, d_workspace, tap_op, d_tap, host_op_ms, st);
+}
+
+static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace, int tap_op,
+                   void* d_tap, float* host_op_ms, cudaStream_t st) {
+  const int n_ops = (int)m->ops.size();
+  const int chunk_seg[2] = {batch < m->chunk ? batch : m->chunk, batch < m->chunk_late ? batch : m->chunk_late};
+  // workspace carve-up: [Xe | Ee | De] (early chunk) [H = late X, whole batch] [El | Dl] (late chunk)
+  uint16_t* base = static_cast<uint16_t*>(d_workspace);
+  uint16_t* early[3];
+  early[0] = base;
+  early[1] = early[0] + m->buf_elems[0][0] * chunk_seg[0];
+  early[2] = early[1] + m->buf_elems[0][1] * chunk_seg[0];
+  uint16_t* H = early[2] + m->buf_elems[0][2] * chunk_seg[0];
+  uint16_t* late_e = H + m->buf_elems[1][0] * (size_t)batch;
+  uint16_t* late_d = late_e + m->buf_elems[1][1] * chunk_seg[1];
+
+  std::vector<cudaEvent_t> evs;
+  size_t ev_i = 0;
+  if (host_op_ms) {
+    size_t n = 0;
+    for (int sgi = 0; sgi < 2; ++sgi) {
+      const int ops_in = sgi == 0 ? m->split_op : n_ops - m->split_op;
+      if (ops_in > 0) n += (size_t)((batch + chunk_seg[sgi] - 1) / chunk_seg[sgi]) * (ops_in + 1);
+    }
+    evs.resize(n);
+    for (auto& e : evs) KWS_CUDA_CHECK(cudaEventCreate(&e));
+    for (int i = 0; i < n_ops; ++i) host_op_ms[i] = 0.f;
+  }
+  std::vector<int> ev_op;   // op index ending at event i (-1 = chunk start marker)
+
+  for (int sgi = 0; sgi < 2; ++sgi) {
+    const int op_lo = sgi == 0 ? 0 : m->split_op, op_hi = sgi == 0 ? m->split_op : n_ops;
+    if (op_lo >= op_hi) continue;
+    const int chunk = chunk_seg[sgi];
+    for (int b0 = 0; b0 < batch; b0 += chunk) {
+      const int nb = batch - b0 < chunk ? batch - b0 : chunk;
+      uint16_t* bufs[3];
+      if (sgi == 0) { bufs[0] = early[0]; bufs[1] = early[1]; bufs[2] = early[2]; }
+      else { bufs[0] = H + m->buf_elems[1][0] * (size_t)b0; bufs[1] = late_e; bufs[2] = late_d; }
+      if (host_op_ms) { KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st)); ev_op.push_back(-1); }
+      for (int oi = op_lo; oi < op_hi; ++oi) {
+        const Op& op = m->ops[oi];
+        void* out_ptr = op.out_buf >= 0 ? (void*)bufs[op.out_buf] : (void*)(d_emb + (size_t)b0 * m->out_dim);
+        if (sgi == 0 && oi == m->split_op - 1 && op.out_buf == 0)      // hand-off: early chunk -> late X (whole batch)
+          out_ptr = H + m->buf_elems[1][0] * (size_t)b0;
+        int rc = KWS_OK;
+        if (op.kind == kOpStem) {
+          rc = launch_stem(d_feats + (size_t)b0 * m->H * m->W, nb, op.stem, out_ptr, m->sm_count, st);
+        } else if (op.kind == kOpDwse) {
+          rc = launch_dwse(bufs[op.in_buf], nb, op.dw, out_ptr, dwse_pick_group(op.dw, m->max_smem, nb, m->sm_count),
+                           m->sm_count, st);
+        } else {
+          GemmShape sh;
+          sh.M = op.rows_per_clip * nb; sh.N = op.N; sh.K = op.K;
+          sh.m_tiles = (sh.M + kGemmBlockM - 1) / kGemmBlockM;
+          sh.block_n = pick_block_n(op.N, sh.m_tiles, m->sm_count);
+          sh.n_tiles = (op.N + sh.block_n - 1) / sh.block_n;
+          const int num_kb = (op.K + kGemmBlockK - 1) / kGemmBlockK;
+          int stages = (int)((200 * 1024) / (kGemmBlockM * kGemmBlockK * 2 + sh.block_n * kGemmBlockK * 2));
+          if (stages > kGemmMaxStages) stages = kGemmMaxStages;
+          if (stages > num_kb + 2) stages = num_kb + 2;
+          if (stages < 2) stages = 2;
+          sh.stages = stages;
+          CUtensorMap ta, tb;
+          rc = make_tmap_h16_kmajor(&ta, bufs[op.in_buf], (uint64_t)sh.M, (uint64_t)op.K, kGemmBlockM, m->bf16);
+          if (rc == KWS_OK) rc = make_tmap_h16_kmajor(&tb, op.w, (uint64_t)op.N, (uint64_t)op.K, (uint32_t)sh.block_n, m->bf16);
+          if (rc == KWS_OK) {
+            GemmEpilogue ep;
+            ep.bias = op.bias;
+            ep.residual = op.res_buf >= 0 ? bufs[op.res_buf] : nullptr;
+            ep.out = out_ptr; ep.ldo = op.N; ep.ldr = op.N;
+            ep.act = op.act; ep.out_f32 = op.out_f32; ep.gap4 = op.gap4; ep.bf16 = m->bf16;
+            rc = launch_gemm_tcgen05(ta, tb, sh, ep, m->sm_count, st);
+          }
+        }
+        if (rc != KWS_OK) return rc;
+        if (host_op_ms) { KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st)); ev_op.push_back(oi); }
+        if (oi == tap_op && d_tap) {
+          const size_t esz = op.out_f32 ? 4 : 2;
+          KWS_CUDA_CHECK(cudaMemcpyAsync(static_cast<uint8_t*>(d_tap) + (size_t)b0 * op.out_elems_per_clip * esz, out_ptr,
+                                         (size_t)nb * op.out_elems_per_clip * esz, cudaMemcpyDeviceToDevice, st));
+        }
       }
     }
   }
   if (host_op_ms) {
     KWS_CUDA_CHECK(cudaStreamSynchronize(st));
-    const size_t per = m->ops.size() + 1;
-    for (size_t c = 0; c * per < evs.size(); ++c)
-      for (size_t i = 0; i < m->ops.size(); ++i) {
+    for (size_t i = 1; i < ev_i; ++i)
+      if (ev_op[i] >= 0) {
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, evs[c * per + i], evs[c * per + i + 1]);
-        host_op_ms[i] += ms;
+        cudaEventElapsedTime(&ms, evs[i - 1], evs[i]);
+        host_op_ms[ev_op[i]] += ms;
       }
     for (auto& e : evs) cudaEventDestroy(e);
   }

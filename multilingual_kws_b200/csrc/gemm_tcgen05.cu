@@ -24,7 +24,7 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int stages) {
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == kActSwish) return x / (1.0f + __expf(-x));
+  if (act == kActSwish) return __fdividef(x, 1.0f + __expf(-x));
   if (act == kActRelu) return fmaxf(x, 0.0f);
   if (act == kActSelu) return x > 0.0f ? 1.0507009873554805f * x : 1.7580993408473766f * (__expf(x) - 1.0f);
   return x;

@@ -99,6 +99,16 @@ class EmbeddingModel:
         _lib.check(_lib.lib().kws_embed_set_chunk(self._h, int(chunk)))
         self._ws = None
 
+    def set_chunk_late(self, chunk: int) -> None:
+        _lib.check(_lib.lib().kws_embed_set_chunk_late(self._h, int(chunk)))
+        self._ws = None
+
+    def launches(self, batch: int) -> int:
+        return int(_lib.lib().kws_embed_launches(self._h, int(batch)))
+
+    def set_graph(self, enable: bool) -> None:
+        _lib.check(_lib.lib().kws_embed_set_graph(self._h, int(bool(enable))))
+
     def op_names(self):
         L = _lib.lib()
         out = []

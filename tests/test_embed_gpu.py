@@ -79,6 +79,12 @@ def test_chunking_and_batch_sizes_agree(setup, feats):
         model.set_chunk(chunk)
         assert torch.equal(model.forward_device(x).cpu(), full)
     model.set_chunk(256)
+    model.set_chunk_late(9)
+    assert torch.equal(model.forward_device(x).cpu(), full)
+    model.set_chunk_late(2048)
+    model.set_graph(False)
+    assert torch.equal(model.forward_device(x).cpu(), full)
+    model.set_graph(True)
     for b in (1, 3, 33):
         assert torch.equal(model.forward_device(x[:b]).cpu(), full[:b])
     assert model.forward_device(x[:0]).shape == (0, 1024)
