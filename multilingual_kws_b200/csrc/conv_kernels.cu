@@ -76,7 +76,7 @@ stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, uint1
 constexpr int kDwThreads = 256;
 
 struct DwSmem {
-  uint32_t in_bytes, out_off, pooled_off, part_off, s_off, bar_off, total;
+  uint32_t in_bytes, out_off, pooled_off, part_off, s_off, red_off, bar_off, total;
   int PL;   // pixel lanes per channel pair
 };
 __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
@@ -88,7 +88,8 @@ __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
   L.pooled_off = L.out_off + (((uint32_t)G * P.Ho * P.Wo * P.C * 2 + 127) & ~127u);
   L.part_off = L.pooled_off + (uint32_t)G * P.C * 4;                       // [PL][G][C] partial channel sums
   L.s_off = L.part_off + (L.PL > 1 ? (uint32_t)L.PL * G * P.C * 4 : 0u);
-  L.bar_off = (L.s_off + (uint32_t)G * P.se * 4 + 15) & ~15u;
+  L.red_off = L.s_off + (uint32_t)G * P.se * 4;                              // [se][8 warps][4 clips] FC1 partials
+  L.bar_off = (L.red_off + (uint32_t)P.se * (kDwThreads / 32) * 4 * 4 + 15) & ~15u;
   L.total = L.bar_off + 16;
   return L;
 }
@@ -103,6 +104,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
   float* s_pool = reinterpret_cast<float*>(smem + L.pooled_off);              // [G][C] sums, later gates
   float* s_part = reinterpret_cast<float*>(smem + L.part_off);                // [PL][G][C] (deterministic pool reduce)
   float* s_se = reinterpret_cast<float*>(smem + L.s_off);                     // [G][se]
+  float* s_red = reinterpret_cast<float*>(smem + L.red_off);                  // [se][warps][4]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -191,30 +193,54 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
       __syncthreads();
     }
 
-    // ---- SE reduce: s[g][j] = swish(b1[j] + mean_g . w1[j][:]); one warp per j, weights read once per group
-    for (int j = warp; j < P.se; j += kDwThreads / 32) {
-      const float* wrow = P.w_se1 + (size_t)j * C;
-      for (int gb = 0; gb < gn; gb += 8) {          // register-block 8 clips per pass over the weight row
-        float acc[8];
+    // ---- SE reduce: s[g][j] = swish(b1[j] + mean_g . w1[j][:]).  Every thread owns channels c = tid + 256 i and
+    // streams its slice of every weight row (coalesced, independent loads -> deep memory-level parallelism);
+    // partial dot products are reduced by warp shuffles, then across the 8 warps through smem.
+    {
+      constexpr int kMaxCi = 5;                                   // ceil(1152 / 256)
+      const int nci = (C + kDwThreads - 1) / kDwThreads;
+      for (int gb = 0; gb < gn; gb += 4) {
+        float pv[4][kMaxCi];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = 0.0f;
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int i = 0; i < kMaxCi; ++i) {
+            const int c = tid + i * kDwThreads;
+            pv[u][i] = (i < nci && c < C && gb + u < gn) ? s_pool[(gb + u) * C + c] : 0.0f;
+          }
 #pragma unroll 4
-        for (int c = lane; c < C; c += 32) {
-          const float wv = __ldg(wrow + c);
+        for (int j = 0; j < P.se; ++j) {
+          const float* wrow = P.w_se1 + (size_t)j * C;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (gb + u < gn) acc[u] = fmaf(wv, s_pool[(gb + u) * C + c], acc[u]);
+          for (int i = 0; i < kMaxCi; ++i) {
+            const int c = tid + i * kDwThreads;
+            if (i < nci && c < C) {
+              const float wv = __ldg(wrow + c);
+              a0 = fmaf(wv, pv[0][i], a0); a1 = fmaf(wv, pv[1][i], a1);
+              a2 = fmaf(wv, pv[2][i], a2); a3 = fmaf(wv, pv[3][i], a3);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+          }
+          if (lane == 0) *reinterpret_cast<float4*>(&s_red[(j * (kDwThreads / 32) + warp) * 4]) = make_float4(a0, a1, a2, a3);
         }
+        __syncthreads();
+        for (int t = tid; t < P.se * 4; t += kDwThreads) {
+          const int j = t >> 2, u = t & 3;
+          if (gb + u < gn) {
+            float a = 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          float a = acc[u];
-#pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-          if (lane == 0 && gb + u < gn) s_se[(gb + u) * P.se + j] = swish(a * inv_npix + __ldg(P.b_se1 + j));
+            for (int wv = 0; wv < kDwThreads / 32; ++wv) a += s_red[(j * (kDwThreads / 32) + wv) * 4 + u];
+            s_se[(gb + u) * P.se + j] = swish(a * inv_npix + __ldg(P.b_se1 + j));
+          }
         }
+        __syncthreads();
       }
     }
-    __syncthreads();
 
     // ---- SE expand: gate[g][c] = sigmoid(b2[c] + s[g] . w2[:][c])  (overwrites the pooled sums)
     for (int c = tid; c < C; c += kDwThreads) {
@@ -223,7 +249,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
         float acc[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc[u] = b2;
-#pragma unroll 8
+#pragma unroll 16
         for (int j = 0; j < P.se; ++j) {
           const float wv = __ldg(P.w_se2 + (size_t)j * C + c);
 #pragma unroll
@@ -274,7 +300,7 @@ int dwse_pick_group(const DwseParams& P, int max_smem, int batch, int sm_count) 
   for (int i = 0; i < 5 && !fit; ++i)
     if ((int)dw_smem(P, cands[i]).total <= max_smem) fit = cands[i];
   if (!fit) return 0;
-  while (fit > 1 && (batch + fit - 1) / fit < 2 * sm_count) fit >>= 1;   // keep every SM busy with >= 2 groups
+  while (fit > 1 && (batch + fit - 1) / fit < sm_count) fit >>= 1;       // at least one group per SM
   return fit;
 }
 

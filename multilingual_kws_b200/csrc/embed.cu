@@ -100,6 +100,7 @@ struct GraphEntry {
 
 struct kws_embed {
   std::vector<GraphEntry> graphs;      // captured forward passes, keyed by (buffers, batch, chunk)
+  cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy stream)
   int use_graph = 1;
   int H = 49, W = 40, out_dim = 0;
   float in_scale = 1.0f / 255.0f, in_shift = 0.0f;
@@ -405,8 +406,18 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
     if ((int)i == m->split_op - 1 && op.out_buf == 0 && op.out_elems_per_clip > m->buf_elems[1][0])
       m->buf_elems[1][0] = op.out_elems_per_clip;
   }
+  // the late X region is addressed compactly at [clip * hand-off elems]: no rounding of buf_elems[1][0], and every
+  // late X tensor must fit the hand-off row
   for (int sgi = 0; sgi < 2; ++sgi)
-    for (int i = 0; i < 3; ++i) m->buf_elems[sgi][i] = round_up(m->buf_elems[sgi][i], 64);
+    for (int i = 0; i < 3; ++i)
+      if (!(sgi == 1 && i == 0)) m->buf_elems[sgi][i] = round_up(m->buf_elems[sgi][i], 64);
+  if (m->split_op > 0 && m->split_op < (int)m->ops.size() &&
+      m->buf_elems[1][0] != m->ops[m->split_op - 1].out_elems_per_clip) {
+    set_error("kws_embed_create: schedule split needs the hand-off tensor to be the largest late trunk tensor");
+    for (void* p : m->dev_allocs) cudaFree(p);
+    delete m;
+    return KWS_ERR_UNSUPPORTED;
+  }
   m->flops_per_clip = 2.0 * macs;
   *out = m;
   return KWS_OK;
@@ -415,6 +426,7 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
 extern "C" void kws_embed_destroy(kws_embed_t* m) {
   if (!m) return;
   for (auto& g : m->graphs) cudaGraphExecDestroy(g.exec);
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   for (void* p : m->dev_allocs) cudaFree(p);
   delete m;
 }
@@ -512,10 +524,11 @@ static int embed_forward_impl(kws_embed_t* m, const float* d_feats, int batch, f
         KWS_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
         return KWS_OK;
       }
-    KWS_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    const int rc = run_ops(m, d_feats, batch, d_emb, d_workspace, -1, nullptr, nullptr, st);
+    if (!m->cap_stream) KWS_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+    KWS_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_ops(m, d_feats, batch, d_emb, d_workspace, -1, nullptr, nullptr, m->cap_stream);
     cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &graph);
     if (rc != KWS_OK) {
       if (graph) cudaGraphDestroy(graph);
       return rc;
