@@ -148,30 +148,57 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
         for (int g = 0; g < gn; ++g) {
           const uint32_t* in_g = s_in + (size_t)g * clip_words + cp;
           float sum0 = 0.0f, sum1 = 0.0f;
-          int ho = pl / P.Wo, wo = pl - (pl / P.Wo) * P.Wo;
-          for (int p = pl; p < npix; p += PL) {
-            float a0 = bias.x, a1 = bias.y;
+          // Row strips with a K x K register window: the pixel lane `pl` owns output rows ho = pl, pl + PL, ...;
+          // along a row the window slides by S columns, so each output costs K*S shared-memory loads instead of K*K.
+          // Window columns live in slot (wo*S + kw) % K; the wo loop is unrolled by K so slots are compile-time.
+          for (int ho = pl; ho < P.Ho; ho += PL) {
+            const uint32_t* rowp[K];
+            bool row_ok[K];
 #pragma unroll
             for (int kh = 0; kh < K; ++kh) {
               const int r = ho * S + kh - P.pad_top;
-              if (r < 0 || r >= P.H) continue;
+              row_ok[kh] = (r >= 0) && (r < P.H);
+              rowp[kh] = in_g + (size_t)(row_ok[kh] ? r : 0) * P.W * C2;
+            }
+            float2 win[K][K];
+            uint32_t* orow = s_out + ((size_t)g * npix + (size_t)ho * P.Wo) * C2 + cp;
+            for (int wo_base = 0; wo_base < P.Wo; wo_base += K) {
 #pragma unroll
-              for (int kw = 0; kw < K; ++kw) {
-                const int c = wo * S + kw - P.pad_left;
-                if (c < 0 || c >= P.W) continue;
-                const uint32_t v = in_g[(r * P.W + c) * C2];
-                const float2 xv = ptx::unpack_h2(v, P.bf16);
-                a0 = fmaf(xv.x, wreg[kh * K + kw].x, a0);
-                a1 = fmaf(xv.y, wreg[kh * K + kw].y, a1);
+              for (int j = 0; j < K; ++j) {
+                const int wo = wo_base + j;
+                if (wo < P.Wo) {
+#pragma unroll
+                  for (int kw = 0; kw < K; ++kw) {
+                    if (kw >= K - S || wo == 0) {                 // new columns (all K of them for the first output)
+                      const int c = wo * S + kw - P.pad_left;
+                      const bool col_ok = (c >= 0) && (c < P.W);
+                      constexpr int dummy = 0; (void)dummy;
+                      const int slot = (j * S + kw) % K;
+#pragma unroll
+                      for (int kh = 0; kh < K; ++kh) {
+                        float2 v = make_float2(0.0f, 0.0f);
+                        if (col_ok && row_ok[kh]) v = ptx::unpack_h2(rowp[kh][c * C2], P.bf16);
+                        win[kh][slot] = v;
+                      }
+                    }
+                  }
+                  float a0 = bias.x, a1 = bias.y;
+#pragma unroll
+                  for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < K; ++kw) {
+                      const int slot = (j * S + kw) % K;
+                      a0 = fmaf(win[kh][slot].x, wreg[kh * K + kw].x, a0);
+                      a1 = fmaf(win[kh][slot].y, wreg[kh * K + kw].y, a1);
+                    }
+                  a0 = swish(a0);
+                  a1 = swish(a1);
+                  sum0 += a0;
+                  sum1 += a1;
+                  orow[(size_t)wo * C2] = ptx::pack_h2(a0, a1, P.bf16);
+                }
               }
             }
-            a0 = swish(a0);
-            a1 = swish(a1);
-            sum0 += a0;
-            sum1 += a1;
-            s_out[((size_t)g * npix + p) * C2 + cp] = ptx::pack_h2(a0, a1, P.bf16);
-            wo += PL;
-            while (wo >= P.Wo) { wo -= P.Wo; ++ho; }
           }
           if (PL == 1) {
             s_pool[g * C + 2 * cp] = sum0;
