@@ -88,7 +88,7 @@ __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
   L.pooled_off = L.out_off + (((uint32_t)G * P.Ho * P.Wo * P.C * 2 + 127) & ~127u);
   L.part_off = L.pooled_off + (uint32_t)G * P.C * 4;                       // [PL][G][C] partial channel sums
   L.s_off = L.part_off + (L.PL > 1 ? (uint32_t)L.PL * G * P.C * 4 : 0u);
-  L.red_off = L.s_off + (uint32_t)G * P.se * 4;                              // [se][8 warps][4 clips] FC1 partials
+  L.red_off = (L.s_off + (uint32_t)G * P.se * 4 + 15) & ~15u;                            // [se][8 warps][4 clips] FC1 partials
   L.bar_off = (L.red_off + (uint32_t)P.se * (kDwThreads / 32) * 4 * 4 + 15) & ~15u;
   L.total = L.bar_off + 16;
   return L;

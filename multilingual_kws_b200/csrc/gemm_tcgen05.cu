@@ -13,13 +13,14 @@ namespace {
 constexpr uint32_t kABytes = kGemmBlockM * kGemmBlockK * 2;   // 16 KiB per stage
 
 struct SmemLayout {
-  uint32_t stage_bytes, bar_off, total;
+  uint32_t stage_bytes, bar_off, bias_off, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int block_n, int stages) {
   SmemLayout L;
   L.stage_bytes = kABytes + (uint32_t)block_n * kGemmBlockK * 2;
   L.bar_off = L.stage_bytes * stages;
-  L.total = L.bar_off + 8 * (2 * kGemmMaxStages + 4) + 16;
+  L.bias_off = L.bar_off + 8 * (2 * kGemmMaxStages + 4) + 16;      // float s_bias[2][256]
+  L.total = L.bias_off + 2 * 256 * 4;
   return L;
 }
 
@@ -41,6 +42,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_full = empty_bar + kGemmMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + L.bias_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int block_n = sh.block_n, stages = sh.stages;
@@ -62,7 +64,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(tmem_full + a, 1);
-        ptx::mbar_init(tmem_empty + a, 4);   // one arrive per epilogue warp
+        ptx::mbar_init(tmem_empty + a, 8);   // one arrive per epilogue warp
       }
       ptx::fence_barrier_init();
     }
@@ -125,40 +127,53 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                     // which of the two warps of this quarter (chunk parity)
+    const int et = (int)threadIdx.x - 64;                 // 0..255 among epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_t = tile / sh.n_tiles, n_t = tile - m_t * sh.n_tiles;
+      // stage this tile's bias slice in smem (removes a global-load latency from every 16-column chunk)
+      float* sb = s_bias + acc * 256;
+      if (et < block_n) {
+        const int n = n_t * block_n + et;
+        sb[et] = (ep.bias && n < sh.N) ? __ldg(ep.bias + n) : 0.0f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // epilogue warps only
       ptx::mbar_wait(tmem_full + acc, acc_phase);
       ptx::tc_fence_after();
       const int row = m_t * kGemmBlockM + q * 32 + lane;
       const bool row_ok = row < sh.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * block_n);
-      for (int c0 = 0; c0 < block_n; c0 += 16) {
+      for (int c0 = half * 16; c0 < block_n; c0 += 32) {
         const int n_base = n_t * block_n + c0;
         if (n_base >= sh.N) break;                        // warp-uniform
         uint32_t r[16];
         ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
+        // residual prefetch while the TMEM load is in flight (plain loads: the residual may alias the output)
+        uint4 rr[2];
+        rr[0] = rr[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (ep.residual && row_ok) {
+          const uint16_t* rp = static_cast<const uint16_t*>(ep.residual) + (size_t)row * ep.ldr + n_base;
+          rr[0] = *reinterpret_cast<const uint4*>(rp);
+          if (n_base + 8 < sh.N) rr[1] = *reinterpret_cast<const uint4*>(rp + 8);
+        }
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int n0 = n_base + 8 * g;
           if (n0 >= sh.N) break;                          // N is a multiple of 8
           float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * g + j]);
-          if (ep.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
+          const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + 8 * g);
+          const float4 b1 = *reinterpret_cast<const float4*>(sb + c0 + 8 * g + 4);
+          v[0] = __uint_as_float(r[8 * g + 0]) + b0.x; v[1] = __uint_as_float(r[8 * g + 1]) + b0.y;
+          v[2] = __uint_as_float(r[8 * g + 2]) + b0.z; v[3] = __uint_as_float(r[8 * g + 3]) + b0.w;
+          v[4] = __uint_as_float(r[8 * g + 4]) + b1.x; v[5] = __uint_as_float(r[8 * g + 5]) + b1.y;
+          v[6] = __uint_as_float(r[8 * g + 6]) + b1.z; v[7] = __uint_as_float(r[8 * g + 7]) + b1.w;
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
           if (ep.residual && row_ok) {
-            // plain (coherent) load: the residual may alias the output buffer (in-place skip connection)
-            const uint4 rr = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(ep.residual) + (size_t)row * ep.ldr + n0);
-            const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+            const uint32_t w[4] = {rr[g].x, rr[g].y, rr[g].z, rr[g].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 f = ptx::unpack_h2(w[j], ep.bf16);

@@ -8,8 +8,9 @@
 //   epilogue: + bias[N] (folded BatchNorm), activation, + residual[M,N], optional 4-row mean (GAP of the
 //   2x2 top activation), store bf16 or fp32.
 //
-// Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane)
-// + TMEM allocation, warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Pipelines: smem ring
+// Roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane)
+// + TMEM allocation, warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter split the
+// 16-column chunks; the tile's bias slice is staged in smem once per tile).  Pipelines: smem ring
 // full/empty mbarriers (TMA <-> MMA), 2 TMEM accumulator stages full/empty (MMA <-> epilogue), so the
 // epilogue of tile i overlaps the loads + MMAs of tile i+1.  Tiles: 128 x BLOCK_N x 64, SWIZZLE_128B.
 #pragma once
@@ -21,7 +22,7 @@ namespace kws {
 
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B atom row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;         // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kGemmMaxStages = 8;
 
 enum GemmAct : int { kActNone = 0, kActSwish = 1, kActRelu = 2, kActSelu = 3 };
