@@ -290,17 +290,30 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
     }
     __syncthreads();
 
-    // ---- scale and store (coalesced 4-byte words; the whole group is one contiguous block of y)
+    // ---- scale and store: 16-byte vectors (8 channels), coalesced; no div/mod in the loop
     {
-      uint32_t* dst = reinterpret_cast<uint32_t*>(y) + (size_t)g0 * npix * C2;
-      const int words = gn * npix * C2;
-      for (int i = tid; i < words; i += kDwThreads) {
-        const int g = i / (npix * C2);
-        const int cpair = i % C2;
-        const uint32_t v = s_out[i];
-        const float2 gate = *reinterpret_cast<const float2*>(&s_pool[g * C + 2 * cpair]);
-        const float2 xv = ptx::unpack_h2(v, P.bf16);
-        dst[i] = ptx::pack_h2(xv.x * gate.x, xv.y * gate.y, P.bf16);
+      const int C8 = C >> 3;                                  // uint4 vectors per pixel
+      const int vec_per_clip = npix * C8;
+      const int step = kDwThreads % C8;
+      for (int g = 0; g < gn; ++g) {
+        const uint4* src = reinterpret_cast<const uint4*>(s_out) + (size_t)g * vec_per_clip;
+        uint4* dst = reinterpret_cast<uint4*>(y) + ((size_t)(g0 + g) * vec_per_clip);
+        const float* gate = s_pool + g * C;
+        int c8 = tid % C8;
+        for (int i = tid; i < vec_per_clip; i += kDwThreads) {
+          const uint4 v = src[i];
+          const float4 g0v = *reinterpret_cast<const float4*>(gate + 8 * c8);
+          const float4 g1v = *reinterpret_cast<const float4*>(gate + 8 * c8 + 4);
+          float2 x;
+          uint4 o;
+          x = ptx::unpack_h2(v.x, P.bf16); o.x = ptx::pack_h2(x.x * g0v.x, x.y * g0v.y, P.bf16);
+          x = ptx::unpack_h2(v.y, P.bf16); o.y = ptx::pack_h2(x.x * g0v.z, x.y * g0v.w, P.bf16);
+          x = ptx::unpack_h2(v.z, P.bf16); o.z = ptx::pack_h2(x.x * g1v.x, x.y * g1v.y, P.bf16);
+          x = ptx::unpack_h2(v.w, P.bf16); o.w = ptx::pack_h2(x.x * g1v.z, x.y * g1v.w, P.bf16);
+          dst[i] = o;
+          c8 += step;
+          if (c8 >= C8) c8 -= C8;
+        }
       }
     }
     __syncthreads();
