@@ -176,21 +176,24 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
                       const int slot = (j * S + kw) % K;
 #pragma unroll
                       for (int kh = 0; kh < K; ++kh) {
+                        if (!row_ok[kh]) continue;
                         float2 v = make_float2(0.0f, 0.0f);
-                        if (col_ok && row_ok[kh]) v = ptx::unpack_h2(rowp[kh][c * C2], P.bf16);
+                        if (col_ok) v = ptx::unpack_h2(rowp[kh][c * C2], P.bf16);
                         win[kh][slot] = v;
                       }
                     }
                   }
                   float a0 = bias.x, a1 = bias.y;
 #pragma unroll
-                  for (int kh = 0; kh < K; ++kh)
+                  for (int kh = 0; kh < K; ++kh) {
+                    if (!row_ok[kh]) continue;                    // padded rows contribute nothing (tiny late maps: most rows)
 #pragma unroll
                     for (int kw = 0; kw < K; ++kw) {
                       const int slot = (j * S + kw) % K;
                       a0 = fmaf(win[kh][slot].x, wreg[kh * K + kw].x, a0);
                       a1 = fmaf(win[kh][slot].y, wreg[kh * K + kw].y, a1);
                     }
+                  }
                   a0 = swish(a0);
                   a1 = swish(a1);
                   sum0 += a0;

@@ -173,21 +173,6 @@ struct Builder {
   const float* vec(const std::vector<float>& v) { return upload(m, v, &cerr); }
 };
 
-int pick_block_n(int N, int m_tiles, int sm_count) {
-  // candidates with little column padding; prefer the largest that still gives every SM a tile
-  const int cands[] = {256, 240, 224, 192, 160, 144, 128, 112, 96, 80, 64, 48, 32, 16};
-  int best = -1;
-  for (int bn : cands) {
-    const int n_tiles = (N + bn - 1) / bn;
-    if (n_tiles * bn - N >= 16 && bn > 16) continue;          // wasteful padding
-    if (best < 0) best = bn;
-    if ((long long)n_tiles * m_tiles >= sm_count) return bn;
-    if (bn <= 64) break;                                       // do not shrink tiles below 64 columns
-    best = bn;
-  }
-  return best > 0 ? best : 16;
-}
-
 }  // namespace
 
 extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t bytes, int act_dtype) {
@@ -599,28 +584,12 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
           rc = launch_dwse(bufs[op.in_buf], nb, op.dw, out_ptr, dwse_pick_group(op.dw, m->max_smem, nb, m->sm_count),
                            m->sm_count, st);
         } else {
-          GemmShape sh;
-          sh.M = op.rows_per_clip * nb; sh.N = op.N; sh.K = op.K;
-          sh.m_tiles = (sh.M + kGemmBlockM - 1) / kGemmBlockM;
-          sh.block_n = pick_block_n(op.N, sh.m_tiles, m->sm_count);
-          sh.n_tiles = (op.N + sh.block_n - 1) / sh.block_n;
-          const int num_kb = (op.K + kGemmBlockK - 1) / kGemmBlockK;
-          int stages = (int)((200 * 1024) / (kGemmBlockM * kGemmBlockK * 2 + sh.block_n * kGemmBlockK * 2));
-          if (stages > kGemmMaxStages) stages = kGemmMaxStages;
-          if (stages > num_kb + 2) stages = num_kb + 2;
-          if (stages < 2) stages = 2;
-          sh.stages = stages;
-          CUtensorMap ta, tb;
-          rc = make_tmap_h16_kmajor(&ta, bufs[op.in_buf], (uint64_t)sh.M, (uint64_t)op.K, kGemmBlockM, m->bf16);
-          if (rc == KWS_OK) rc = make_tmap_h16_kmajor(&tb, op.w, (uint64_t)op.N, (uint64_t)op.K, (uint32_t)sh.block_n, m->bf16);
-          if (rc == KWS_OK) {
-            GemmEpilogue ep;
-            ep.bias = op.bias;
-            ep.residual = op.res_buf >= 0 ? bufs[op.res_buf] : nullptr;
-            ep.out = out_ptr; ep.ldo = op.N; ep.ldr = op.N;
-            ep.act = op.act; ep.out_f32 = op.out_f32; ep.gap4 = op.gap4; ep.bf16 = m->bf16;
-            rc = launch_gemm_tcgen05(ta, tb, sh, ep, m->sm_count, st);
-          }
+          GemmEpilogue ep;
+          ep.bias = op.bias;
+          ep.residual = op.res_buf >= 0 ? bufs[op.res_buf] : nullptr;
+          ep.out = out_ptr; ep.ldo = op.N; ep.ldr = op.N;
+          ep.act = op.act; ep.out_f32 = op.out_f32; ep.gap4 = op.gap4; ep.bf16 = m->bf16;
+          rc = gemm_h16(bufs[op.in_buf], op.w, op.rows_per_clip * nb, op.N, op.K, 0, ep, m->sm_count, st);
         }
         if (rc != KWS_OK) return rc;
         if (host_op_ms) { KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st)); ev_op.push_back(oi); }
@@ -672,24 +641,8 @@ extern "C" int kws_gemm_h16(const void* d_a, const void* d_w, int M, int N, int 
   if (M == 0) return KWS_OK;
   const int sm = device_sm_count();
   KWS_REQUIRE(sm > 0, "kws_gemm_h16: CUDA device required; there is no CPU fallback");
-  GemmShape sh;
-  sh.M = M; sh.N = N; sh.K = K;
-  sh.m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
-  sh.block_n = block_n > 0 ? block_n : pick_block_n(N, sh.m_tiles, sm);
-  sh.n_tiles = (N + sh.block_n - 1) / sh.block_n;
-  const int num_kb = (K + kGemmBlockK - 1) / kGemmBlockK;
-  int stages = (int)((200 * 1024) / (kGemmBlockM * kGemmBlockK * 2 + sh.block_n * kGemmBlockK * 2));
-  if (stages > kGemmMaxStages) stages = kGemmMaxStages;
-  if (stages > num_kb + 2) stages = num_kb + 2;
-  if (stages < 2) stages = 2;
-  sh.stages = stages;
-  CUtensorMap ta, tb;
-  int rc = make_tmap_h16_kmajor(&ta, d_a, (uint64_t)M, (uint64_t)K, kGemmBlockM, dtype);
-  if (rc != KWS_OK) return rc;
-  rc = make_tmap_h16_kmajor(&tb, d_w, (uint64_t)N, (uint64_t)K, (uint32_t)sh.block_n, dtype);
-  if (rc != KWS_OK) return rc;
   GemmEpilogue ep;
   ep.bias = d_bias; ep.residual = d_residual;
   ep.out = d_out; ep.ldo = N; ep.ldr = N; ep.act = act; ep.out_f32 = out_f32; ep.gap4 = gap4; ep.bf16 = dtype;
-  return launch_gemm_tcgen05(ta, tb, sh, ep, sm, (cudaStream_t)stream);
+  return gemm_h16(d_a, d_w, M, N, K, block_n, ep, sm, (cudaStream_t)stream);
 }

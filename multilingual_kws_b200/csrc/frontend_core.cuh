@@ -70,29 +70,45 @@ KWS_HD cpx cadd(cpx a, cpx b) { cpx c; c.r = wrap16(a.r + b.r); c.i = wrap16(a.i
 KWS_HD cpx csub(cpx a, cpx b) { cpx c; c.r = wrap16(a.r - b.r); c.i = wrap16(a.i - b.i); return c; }
 KWS_HD cpx fixdiv(cpx a, int32_t mult) { cpx c; c.r = sround(a.r * mult); c.i = sround(a.i * mult); return c; }
 
+// Range analysis that lets most int16 re-wraps be dropped (a wrap is the identity when the value fits):
+//   C_FIXDIV(x, 4):  |sround(x*8191)| <= 8191 for every int16 x;   C_FIXDIV(x, 2): <= 16383.
+//   C_MUL(f, tw) with |f.r|,|f.i| <= 8191 and |tw| <= 32768:  |result| <= 8191*sqrt(2)+1 = 11585.
+//   s5 = f0 - s1, f0 + s1: <= 19776;  s3 = s0 + s2, s4 = s0 - s2: <= 23170 — all inside int16.
+//   Only the four final sums (up to 42946) can leave int16, and those keep their wrap.
+KWS_HD int32_t sround_nw(int32_t x) { return (x + 16384) >> 15; }
+KWS_HD cpx cmul_nw(cpx a, cpx b) {
+  cpx m;
+  m.r = sround_nw(a.r * b.r - a.i * b.i);
+  m.i = sround_nw(a.r * b.i + a.i * b.r);
+  return m;
+}
+KWS_HD cpx fixdiv_nw(cpx a, int32_t mult) { cpx c; c.r = sround_nw(a.r * mult); c.i = sround_nw(a.i * mult); return c; }
+
 // kissfft kf_bfly4 body for one k (forward transform), with the C_FIXDIV(.,4) prologue.
 KWS_HD void bfly4(cpx& f0, cpx& f1, cpx& f2, cpx& f3, cpx tw1, cpx tw2, cpx tw3) {
-  f0 = fixdiv(f0, 8191); f1 = fixdiv(f1, 8191); f2 = fixdiv(f2, 8191); f3 = fixdiv(f3, 8191);
-  cpx s0 = cmul(f1, tw1), s1 = cmul(f2, tw2), s2 = cmul(f3, tw3);
-  cpx s5 = csub(f0, s1);
-  f0 = cadd(f0, s1);
-  cpx s3 = cadd(s0, s2), s4 = csub(s0, s2);
-  f2 = csub(f0, s3);
-  f0 = cadd(f0, s3);
-  f1.r = wrap16(s5.r + s4.i); f1.i = wrap16(s5.i - s4.r);
-  f3.r = wrap16(s5.r - s4.i); f3.i = wrap16(s5.i + s4.r);
+  f0 = fixdiv_nw(f0, 8191); f1 = fixdiv_nw(f1, 8191); f2 = fixdiv_nw(f2, 8191); f3 = fixdiv_nw(f3, 8191);
+  const cpx s0 = cmul_nw(f1, tw1), s1 = cmul_nw(f2, tw2), s2 = cmul_nw(f3, tw3);
+  const int32_t s5r = f0.r - s1.r, s5i = f0.i - s1.i;
+  const int32_t t0r = f0.r + s1.r, t0i = f0.i + s1.i;
+  const int32_t s3r = s0.r + s2.r, s3i = s0.i + s2.i;
+  const int32_t s4r = s0.r - s2.r, s4i = s0.i - s2.i;
+  f2.r = wrap16(t0r - s3r); f2.i = wrap16(t0i - s3i);
+  f0.r = wrap16(t0r + s3r); f0.i = wrap16(t0i + s3i);
+  f1.r = wrap16(s5r + s4i); f1.i = wrap16(s5i - s4r);
+  f3.r = wrap16(s5r - s4i); f3.i = wrap16(s5i + s4r);
 }
 // Same butterfly when all three twiddles are tw[0] = (32767, 0).  After C_FIXDIV(.,4) every
-// component satisfies |x| <= 8192, for which sround(x*32767) == x, so the C_MULs are identities.
+// component satisfies |x| <= 8191, for which sround(x*32767) == x, so the C_MULs are identities.
 KWS_HD void bfly4_unit(cpx& f0, cpx& f1, cpx& f2, cpx& f3) {
-  f0 = fixdiv(f0, 8191); f1 = fixdiv(f1, 8191); f2 = fixdiv(f2, 8191); f3 = fixdiv(f3, 8191);
-  cpx s5 = csub(f0, f2);
-  f0 = cadd(f0, f2);
-  cpx s3 = cadd(f1, f3), s4 = csub(f1, f3);
-  f2 = csub(f0, s3);
-  f0 = cadd(f0, s3);
-  f1.r = wrap16(s5.r + s4.i); f1.i = wrap16(s5.i - s4.r);
-  f3.r = wrap16(s5.r - s4.i); f3.i = wrap16(s5.i + s4.r);
+  f0 = fixdiv_nw(f0, 8191); f1 = fixdiv_nw(f1, 8191); f2 = fixdiv_nw(f2, 8191); f3 = fixdiv_nw(f3, 8191);
+  const int32_t s5r = f0.r - f2.r, s5i = f0.i - f2.i;
+  const int32_t t0r = f0.r + f2.r, t0i = f0.i + f2.i;
+  const int32_t s3r = f1.r + f3.r, s3i = f1.i + f3.i;
+  const int32_t s4r = f1.r - f3.r, s4i = f1.i - f3.i;
+  f2.r = t0r - s3r; f2.i = t0i - s3i;          // four terms of magnitude <= 8191: no wrap possible
+  f0.r = t0r + s3r; f0.i = t0i + s3i;
+  f1.r = s5r + s4i; f1.i = s5i - s4r;
+  f3.r = s5r - s4i; f3.i = s5i + s4r;
 }
 
 KWS_HD int msb32(uint32_t x) {
@@ -142,8 +158,8 @@ KWS_HD void fe_p0_window(int lane, const uint32_t* frame_words, const FrontendTa
     if (wi < nwords) {
       const uint32_t s = frame_words[wi];
       const uint32_t c = T.window_pairs[wi];
-      int32_t a = wrap16((lo16(s) * lo16(c)) >> 12);
-      int32_t b = wrap16((hi16(s) * hi16(c)) >> 12);   // coef is 0 past window_size
+      int32_t a = (lo16(s) * lo16(c)) >> 12;           // |s| <= 32768, 0 <= coef <= 4096: always inside int16
+      int32_t b = (hi16(s) * hi16(c)) >> 12;           // coef is 0 past window_size
       out = pack16(a, b);
       int32_t aa = a < 0 ? wrap16(-a) : a;               // int16 negate: -(-32768) stays negative
       int32_t bb = b < 0 ? wrap16(-b) : b;
@@ -220,12 +236,14 @@ KWS_HD void fe_p3_real_energy(int lane, const uint32_t* fftbuf, const uint32_t* 
     cpx fpk = unpack(fftbuf[fft_pad(k)]);
     cpx t = unpack(fftbuf[fft_pad((256 - k) & 255)]);
     cpx fpnk; fpnk.r = t.r; fpnk.i = wrap16(-t.i);
-    fpk = fixdiv(fpk, 16383);
-    fpnk = fixdiv(fpnk, 16383);
-    const cpx f1k = cadd(fpk, fpnk), f2k = csub(fpk, fpnk);
-    const cpx tw = cmul(f2k, unpack(super_tw[k - 1]));
-    const int32_t ar = wrap16((f1k.r + tw.r) >> 1), ai = wrap16((f1k.i + tw.i) >> 1);
-    const int32_t br = wrap16((f1k.r - tw.r) >> 1), bi = wrap16((tw.i - f1k.i) >> 1);
+    fpk = fixdiv_nw(fpk, 16383);                 // |.| <= 16383: sums / differences below stay inside int16
+    fpnk = fixdiv_nw(fpnk, 16383);
+    cpx f1k, f2k;
+    f1k.r = fpk.r + fpnk.r; f1k.i = fpk.i + fpnk.i;
+    f2k.r = fpk.r - fpnk.r; f2k.i = fpk.i - fpnk.i;
+    const cpx tw = cmul(f2k, unpack(super_tw[k - 1]));      // up to 46338: C_MUL's int16 store wraps
+    const int32_t ar = (f1k.r + tw.r) >> 1, ai = (f1k.i + tw.i) >> 1;   // |sum| <= 65534 -> halves fit int16
+    const int32_t br = (f1k.r - tw.r) >> 1, bi = (tw.i - f1k.i) >> 1;
     const uint32_t ea = (uint32_t)(ar * ar) + (uint32_t)(ai * ai);
     const uint32_t eb = (uint32_t)(br * br) + (uint32_t)(bi * bi);
     if (k != 128) energy[k] = ea;     // for k == ncfft/2 the second store wins in kiss_fftr

@@ -13,13 +13,16 @@ namespace {
 constexpr uint32_t kABytes = kGemmBlockM * kGemmBlockK * 2;   // 16 KiB per stage
 
 struct SmemLayout {
-  uint32_t stage_bytes, bar_off, bias_off, total;
+  uint32_t stage_bytes, staging_off, staging_bytes, bar_off, bias_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int block_n, int stages) {
+// staging: the output tile in TMA-store layout: ceil(block_n / 64) boxes of [rows_box][64] 16-bit, SWIZZLE_128B
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int stages, int staging_rows) {
   SmemLayout L;
   L.stage_bytes = kABytes + (uint32_t)block_n * kGemmBlockK * 2;
-  L.bar_off = L.stage_bytes * stages;
-  L.bias_off = L.bar_off + 8 * (2 * kGemmMaxStages + 4) + 16;      // float s_bias[2][256]
+  L.staging_off = L.stage_bytes * stages;                              // multiple of 1024
+  L.staging_bytes = (uint32_t)((block_n + 63) / 64) * staging_rows * 128;
+  L.bar_off = L.staging_off + L.staging_bytes;
+  L.bias_off = L.bar_off + 8 * (2 * kGemmMaxStages + 4) + 16;          // float s_bias[2][256]
   L.total = L.bias_off + 2 * 256 * 4;
   return L;
 }
@@ -28,15 +31,99 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == kActSwish) return __fdividef(x, 1.0f + __expf(-x));
   if (act == kActRelu) return fmaxf(x, 0.0f);
   if (act == kActSelu) return x > 0.0f ? 1.0507009873554805f * x : 1.7580993408473766f * (__expf(x) - 1.0f);
+  if (act == kActSigmoid) return __fdividef(1.0f, 1.0f + __expf(-x));
   return x;
+}
+
+struct EpiCtx {
+  const GemmShape& sh;
+  const GemmEpilogue& ep;
+  const float* sb;          // this tile's bias slice in smem
+  uint8_t* staging;         // nullptr -> direct global stores
+  int n_t, row, lane, q;
+  bool row_ok;
+};
+
+// One 16-column chunk of one accumulator row: bias, activation, residual, optional 4-row mean, store.
+__device__ __forceinline__ void epilogue_chunk(const EpiCtx& c, const uint32_t (&r)[16], int c0) {
+  const GemmShape& sh = c.sh;
+  const GemmEpilogue& ep = c.ep;
+  const int n_base = c.n_t * sh.block_n + c0;
+  uint4 rr[2];
+  rr[0] = rr[1] = make_uint4(0u, 0u, 0u, 0u);
+  if (ep.residual && c.row_ok) {     // plain (coherent) loads: the residual may alias the output (in-place skip)
+    const uint16_t* rp = static_cast<const uint16_t*>(ep.residual) + (size_t)c.row * ep.ldr + n_base;
+    rr[0] = *reinterpret_cast<const uint4*>(rp);
+    if (n_base + 8 < sh.N) rr[1] = *reinterpret_cast<const uint4*>(rp + 8);
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int n0 = n_base + 8 * g;
+    if (n0 >= sh.N) break;                          // N is a multiple of 8
+    float v[8];
+    const float4 b0 = *reinterpret_cast<const float4*>(c.sb + c0 + 8 * g);
+    const float4 b1 = *reinterpret_cast<const float4*>(c.sb + c0 + 8 * g + 4);
+    v[0] = __uint_as_float(r[8 * g + 0]) + b0.x; v[1] = __uint_as_float(r[8 * g + 1]) + b0.y;
+    v[2] = __uint_as_float(r[8 * g + 2]) + b0.z; v[3] = __uint_as_float(r[8 * g + 3]) + b0.w;
+    v[4] = __uint_as_float(r[8 * g + 4]) + b1.x; v[5] = __uint_as_float(r[8 * g + 5]) + b1.y;
+    v[6] = __uint_as_float(r[8 * g + 6]) + b1.z; v[7] = __uint_as_float(r[8 * g + 7]) + b1.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
+    if (ep.residual && c.row_ok) {
+      const uint32_t w[4] = {rr[g].x, rr[g].y, rr[g].z, rr[g].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = ptx::unpack_h2(w[j], ep.bf16);
+        v[2 * j] += f.x;
+        v[2 * j + 1] += f.y;
+      }
+    }
+    int orow = c.row;                               // global output row
+    int srow = c.q * 32 + c.lane;                   // row inside the staged tile
+    bool store = c.row_ok;
+    if (ep.gap4) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
+        v[j] += __shfl_xor_sync(0xffffffffu, v[j], 2);
+        v[j] *= 0.25f;
+      }
+      orow = c.row >> 2;
+      srow >>= 2;
+      store = c.row_ok && ((c.lane & 3) == 0);
+    }
+    if (ep.out_f32) {
+      if (store) {
+        float* o = reinterpret_cast<float*>(ep.out) + (size_t)orow * ep.ldo + n0;
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    } else {
+      uint4 pk;
+      pk.x = ptx::pack_h2(v[0], v[1], ep.bf16); pk.y = ptx::pack_h2(v[2], v[3], ep.bf16);
+      pk.z = ptx::pack_h2(v[4], v[5], ep.bf16); pk.w = ptx::pack_h2(v[6], v[7], ep.bf16);
+      if (c.staging) {
+        // SWIZZLE_128B staging tile: box = 64 columns; 16-byte piece index XORed with (row & 7)
+        const int col = c0 + 8 * g;
+        const int rows_box = ep.gap4 ? kGemmBlockM / 4 : kGemmBlockM;
+        uint8_t* p = c.staging + (size_t)(col >> 6) * rows_box * 128 + (size_t)srow * 128 +
+                     ((((col & 63) >> 3) ^ (srow & 7)) << 4);
+        if (!ep.gap4 || (c.lane & 3) == 0) *reinterpret_cast<uint4*>(p) = pk;   // rows past M are clipped by the TMA store
+      } else if (store) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out) + (size_t)orow * ep.ldo + n0) = pk;
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmShape sh, const GemmEpilogue ep) {
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmShape sh, const GemmEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const SmemLayout L = smem_layout(sh.block_n, sh.stages);
+  const int staging_rows = sh.tma_store ? (ep.gap4 ? kGemmBlockM / 4 : kGemmBlockM) : 0;
+  const SmemLayout L = smem_layout(sh.block_n, sh.stages, staging_rows);
+  uint8_t* staging = sh.tma_store ? smem + L.staging_off : nullptr;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + kGemmMaxStages;
   uint64_t* tmem_full = empty_bar + kGemmMaxStages;
@@ -55,6 +142,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmap_a);
     ptx::tma_prefetch_desc(&tmap_b);
+    if (sh.tma_store) ptx::tma_prefetch_desc(&tmap_out);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -125,7 +213,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> (smem staging -> TMA store | global) =====================
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;                     // which of the two warps of this quarter (chunk parity)
     const int et = (int)threadIdx.x - 64;                 // 0..255 among epilogue threads
@@ -133,87 +221,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_t = tile / sh.n_tiles, n_t = tile - m_t * sh.n_tiles;
-      // stage this tile's bias slice in smem (removes a global-load latency from every 16-column chunk)
       float* sb = s_bias + acc * 256;
       if (et < block_n) {
         const int n = n_t * block_n + et;
         sb[et] = (ep.bias && n < sh.N) ? __ldg(ep.bias + n) : 0.0f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");      // epilogue warps only
+      if (staging && et == 0) ptx::tma_store_wait_read();  // previous tile's TMA stores have drained the staging tile
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // epilogue warps only
       ptx::mbar_wait(tmem_full + acc, acc_phase);
       ptx::tc_fence_after();
-      const int row = m_t * kGemmBlockM + q * 32 + lane;
-      const bool row_ok = row < sh.M;
+      EpiCtx ctx{sh, ep, sb, staging, n_t, m_t * kGemmBlockM + q * 32 + lane, lane, q, false};
+      ctx.row_ok = ctx.row < sh.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * block_n);
-      for (int c0 = half * 16; c0 < block_n; c0 += 32) {
-        const int n_base = n_t * block_n + c0;
-        if (n_base >= sh.N) break;                        // warp-uniform
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
-        // residual prefetch while the TMEM load is in flight (plain loads: the residual may alias the output)
-        uint4 rr[2];
-        rr[0] = rr[1] = make_uint4(0u, 0u, 0u, 0u);
-        if (ep.residual && row_ok) {
-          const uint16_t* rp = static_cast<const uint16_t*>(ep.residual) + (size_t)row * ep.ldr + n_base;
-          rr[0] = *reinterpret_cast<const uint4*>(rp);
-          if (n_base + 8 < sh.N) rr[1] = *reinterpret_cast<const uint4*>(rp + 8);
-        }
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int n0 = n_base + 8 * g;
-          if (n0 >= sh.N) break;                          // N is a multiple of 8
-          float v[8];
-          const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + 8 * g);
-          const float4 b1 = *reinterpret_cast<const float4*>(sb + c0 + 8 * g + 4);
-          v[0] = __uint_as_float(r[8 * g + 0]) + b0.x; v[1] = __uint_as_float(r[8 * g + 1]) + b0.y;
-          v[2] = __uint_as_float(r[8 * g + 2]) + b0.z; v[3] = __uint_as_float(r[8 * g + 3]) + b0.w;
-          v[4] = __uint_as_float(r[8 * g + 4]) + b1.x; v[5] = __uint_as_float(r[8 * g + 5]) + b1.y;
-          v[6] = __uint_as_float(r[8 * g + 6]) + b1.z; v[7] = __uint_as_float(r[8 * g + 7]) + b1.w;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
-          if (ep.residual && row_ok) {
-            const uint32_t w[4] = {rr[g].x, rr[g].y, rr[g].z, rr[g].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = ptx::unpack_h2(w[j], ep.bf16);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
-            }
-          }
-          int orow = row;
-          bool store = row_ok;
-          if (ep.gap4) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
-              v[j] += __shfl_xor_sync(0xffffffffu, v[j], 2);
-              v[j] *= 0.25f;
-            }
-            orow = row >> 2;
-            store = row_ok && ((lane & 3) == 0);
-          }
-          if (store) {
-            if (ep.out_f32) {
-              float* o = reinterpret_cast<float*>(ep.out) + (size_t)orow * ep.ldo + n0;
-              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-              uint16_t* o = reinterpret_cast<uint16_t*>(ep.out) + (size_t)orow * ep.ldo + n0;
-              uint4 pk;
-              pk.x = ptx::pack_h2(v[0], v[1], ep.bf16); pk.y = ptx::pack_h2(v[2], v[3], ep.bf16);
-              pk.z = ptx::pack_h2(v[4], v[5], ep.bf16); pk.w = ptx::pack_h2(v[6], v[7], ep.bf16);
-              *reinterpret_cast<uint4*>(o) = pk;
-            }
-          }
+      const int n_lim = min(block_n, sh.N - n_t * block_n);  // valid columns of this tile
+      // software-pipelined: the TMEM load of chunk i+1 is in flight while chunk i is processed
+      uint32_t ra[16], rb[16];
+      int c0 = half * 16;
+      if (c0 < n_lim) {
+        ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, ra);
+        for (;;) {
+          ptx::tmem_ld_wait();
+          const int c1 = c0 + 32;
+          if (c1 < n_lim) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c1, rb);
+          epilogue_chunk(ctx, ra, c0);
+          if (c1 >= n_lim) break;
+          ptx::tmem_ld_wait();
+          c0 = c1 + 32;
+          if (c0 < n_lim) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, ra);
+          epilogue_chunk(ctx, rb, c1);
+          if (c0 >= n_lim) break;
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tmem_empty + acc);
+      if (lane == 0) ptx::mbar_arrive(tmem_empty + acc);   // TMEM stage may be overwritten by the next-but-one tile
+      if (staging) {
+        ptx::fence_proxy_async();                          // make this thread's smem writes visible to the TMA engine
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (et == 0) {
+          const int rows_box = ep.gap4 ? kGemmBlockM / 4 : kGemmBlockM;
+          const int n_boxes = (n_lim + 63) >> 6;
+          for (int j = 0; j < n_boxes; ++j)
+            ptx::tma_store_2d(&tmap_out, staging + (size_t)j * rows_box * 128, n_t * block_n + 64 * j, m_t * rows_box);
+          ptx::tma_store_commit();
+        }
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (staging && et == 0) ptx::tma_store_wait_all();     // global writes complete before the kernel exits
   }
 
   ptx::tc_fence_before();
@@ -240,11 +296,35 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Tile width by a small cost model: a CTA streams num_kb k-blocks of (16 KB A + bn*128 B W) per tile at roughly
+// 60 KB/us and spends ~0.01 us per output column in the epilogue; tiles are spread over the SMs in waves.
+// Few-tile problems (late layers, dense tower) get narrow tiles so all SMs work; big-M problems get the widest
+// tile with little column padding.  With several n-tiles the TMA-store boxes (64 columns) must not cross into
+// the neighbouring tile, so block_n is then a multiple of 64.
+int pick_block_n(int N, int K, int m_tiles, int sm_count, bool tma_store) {
+  const int num_kb = (K + kGemmBlockK - 1) / kGemmBlockK;
+  int best = 16;
+  double best_cost = 1e30;
+  for (int bn = 16; bn <= 256; bn += 16) {
+    const int n_tiles = (N + bn - 1) / bn;
+    if (tma_store && n_tiles > 1 && (bn & 63)) continue;
+    const long long tiles = (long long)n_tiles * m_tiles;
+    const long long waves = (tiles + sm_count - 1) / sm_count;
+    const double load_us = num_kb * (16.0 + bn * 0.128) / 60.0;
+    const double epi_us = bn * 0.01;
+    const double tile_us = (load_us > epi_us ? load_us : epi_us) + 0.8;
+    const double cost = waves * tile_us;
+    if (cost < best_cost * 0.97 || (cost < best_cost && bn > best)) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
 }  // namespace
 
-size_t gemm_smem_bytes(int block_n, int stages) { return smem_layout(block_n, stages).total + 1024; }
-
-int make_tmap_h16_kmajor(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bf16) {
+int make_tmap_h16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bf16) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is unavailable (CUDA driver too old or no device)");
@@ -257,9 +337,9 @@ int make_tmap_h16_kmajor(CUtensorMap* out, const void* base, uint64_t rows, uint
   const cuuint64_t gstride[1] = {cols * 2};
   const cuuint32_t box[2] = {(cuuint32_t)kGemmBlockK, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu box_rows %u)", (int)r,
               (unsigned long long)rows, (unsigned long long)cols, box_rows);
@@ -268,22 +348,53 @@ int make_tmap_h16_kmajor(CUtensorMap* out, const void* base, uint64_t rows, uint
   return KWS_OK;
 }
 
-int launch_gemm_tcgen05(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmShape& shape,
-                        const GemmEpilogue& ep, int sm_count, cudaStream_t stream) {
-  KWS_REQUIRE(shape.block_n % 16 == 0 && shape.block_n >= 16 && shape.block_n <= 256, "gemm: bad block_n %d", shape.block_n);
-  KWS_REQUIRE(shape.stages >= 2 && shape.stages <= kGemmMaxStages, "gemm: bad stage count %d", shape.stages);
-  KWS_REQUIRE(shape.N % 8 == 0 && shape.K % 8 == 0, "gemm: N (%d) and K (%d) must be multiples of 8", shape.N, shape.K);
-  KWS_REQUIRE(!ep.gap4 || shape.M % 4 == 0, "gemm: gap4 epilogue needs M %% 4 == 0");
-  if (shape.M == 0) return KWS_OK;
-  const size_t smem = gemm_smem_bytes(shape.block_n, shape.stages);
+int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, const GemmEpilogue& ep_in, int sm_count,
+             cudaStream_t stream) {
+  KWS_REQUIRE(N % 8 == 0 && K % 8 == 0 && N > 0 && K > 0, "gemm: N (%d) and K (%d) must be positive multiples of 8", N, K);
+  KWS_REQUIRE(!ep_in.gap4 || M % 4 == 0, "gemm: gap4 epilogue needs M %% 4 == 0");
+  if (M == 0) return KWS_OK;
+  GemmEpilogue ep = ep_in;
+  GemmShape sh;
+  sh.M = M; sh.N = N; sh.K = K;
+  sh.m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
+  // 16-bit outputs go through a swizzled smem tile and TMA stores (full 128-byte lines); fp32 outputs (the final
+  // embedding only) and non-dense outputs use direct stores.  Residual reads and the store of one tile touch
+  // exactly the same elements, so the in-place skip connection stays race-free.
+  sh.tma_store = (ep.out_f32 || ep.ldo != N) ? 0 : 1;
+  sh.block_n = block_n > 0 ? block_n : pick_block_n(N, K, sh.m_tiles, sm_count, sh.tma_store != 0);
+  KWS_REQUIRE(sh.block_n % 16 == 0 && sh.block_n >= 16 && sh.block_n <= 256, "gemm: bad block_n %d", sh.block_n);
+  sh.n_tiles = (N + sh.block_n - 1) / sh.block_n;
+  if (sh.tma_store && sh.n_tiles > 1 && (sh.block_n & 63)) sh.tma_store = 0;   // forced odd tile width: direct stores
+  const int staging_rows = sh.tma_store ? (ep.gap4 ? kGemmBlockM / 4 : kGemmBlockM) : 0;
+  const int num_kb = (K + kGemmBlockK - 1) / kGemmBlockK;
+  const size_t budget = 220 * 1024;
+  int stages = kGemmMaxStages;
+  while (stages > 2 && smem_layout(sh.block_n, stages, staging_rows).total + 1024 > budget) --stages;
+  if (stages > num_kb + 2) stages = num_kb + 2;
+  if (stages < 2) stages = 2;
+  sh.stages = stages;
+  const size_t smem = smem_layout(sh.block_n, sh.stages, staging_rows).total + 1024;
+  KWS_REQUIRE(smem <= 227 * 1024, "gemm: tile configuration does not fit shared memory");
+
+  CUtensorMap ta, tb, tout;
+  int rc = make_tmap_h16(&ta, a, (uint64_t)M, (uint64_t)K, kGemmBlockM, ep.bf16);
+  if (rc != KWS_OK) return rc;
+  rc = make_tmap_h16(&tb, w, (uint64_t)N, (uint64_t)K, (uint32_t)sh.block_n, ep.bf16);
+  if (rc != KWS_OK) return rc;
+  if (sh.tma_store) {
+    rc = make_tmap_h16(&tout, ep.out, (uint64_t)(ep.gap4 ? M / 4 : M), (uint64_t)N, (uint32_t)staging_rows, ep.bf16);
+    if (rc != KWS_OK) return rc;
+  } else {
+    tout = ta;   // unused
+  }
   static size_t configured = 0;
   if (smem > configured) {
     KWS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const int tiles = shape.m_tiles * shape.n_tiles;
+  const int tiles = sh.m_tiles * sh.n_tiles;
   const int grid = tiles < sm_count ? tiles : sm_count;
-  gemm_tcgen05_kernel<<<grid, kGemmThreads, smem, stream>>>(tmap_a, tmap_b, shape, ep);
+  gemm_tcgen05_kernel<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tout, sh, ep);
   KWS_CUDA_CHECK(cudaGetLastError());
   return KWS_OK;
 }

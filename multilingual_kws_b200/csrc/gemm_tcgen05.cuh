@@ -6,7 +6,8 @@
 //
 //   D[M,N] = epilogue( A[M,K] (fp16|bf16, K-major) x W[N,K]^T (same type, K-major) )      fp32 accumulate in TMEM
 //   epilogue: + bias[N] (folded BatchNorm), activation, + residual[M,N], optional 4-row mean (GAP of the
-//   2x2 top activation), store bf16 or fp32.
+//   2x2 top activation); 16-bit outputs are staged in a SWIZZLE_128B smem tile and written with TMA stores
+//   (full 128-byte lines, clipped at the tensor bounds), fp32 outputs with direct 16-byte stores.
 //
 // Roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane)
 // + TMEM allocation, warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter split the
@@ -25,7 +26,7 @@ constexpr int kGemmBlockK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B 
 constexpr int kGemmThreads = 320;         // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kGemmMaxStages = 8;
 
-enum GemmAct : int { kActNone = 0, kActSwish = 1, kActRelu = 2, kActSelu = 3 };
+enum GemmAct : int { kActNone = 0, kActSwish = 1, kActRelu = 2, kActSelu = 3, kActSigmoid = 4 };
 
 struct GemmEpilogue {
   const float* bias;                 // [N] or nullptr
@@ -43,15 +44,15 @@ struct GemmShape {
   int block_n;                       // multiple of 16, <= 256
   int stages;
   int m_tiles, n_tiles;
+  int tma_store;                     // 1: epilogue stages the tile in swizzled smem and writes it with TMA stores
 };
 
-// Host: launch on `stream`.  tmap_a: [M,K] box {64,128}; tmap_b: [N,K] box {64,block_n}; both SWIZZLE_128B.
-int launch_gemm_tcgen05(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmShape& shape,
-                        const GemmEpilogue& ep, int sm_count, cudaStream_t stream);
+// Host: build the tensor maps, pick the tile shape (block_n = 0 -> cost model) and launch on `stream`.
+// a: [M,K], w: [N,K] 16-bit K-major device pointers.
+int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, const GemmEpilogue& ep, int sm_count,
+             cudaStream_t stream);
 
-// Host: 2-D bf16 K-major tensor map, box = {64, box_rows}, 128B swizzle, zero OOB fill.
-int make_tmap_h16_kmajor(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bf16);
-
-size_t gemm_smem_bytes(int block_n, int stages);
+// Host: 2-D 16-bit tensor map [rows, cols] (cols contiguous), box = {64, box_rows}, 128B swizzle, zero OOB fill.
+int make_tmap_h16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bf16);
 
 }  // namespace kws

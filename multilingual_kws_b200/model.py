@@ -193,13 +193,14 @@ class EmbeddingModel:
 
 def gemm_h16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0,
              residual: Optional[torch.Tensor] = None, out_f32: bool = False, gap4: bool = False,
-             block_n: int = 0) -> torch.Tensor:
+             block_n: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The tcgen05 pointwise/dense operator: act(a @ w.T + bias) (+ residual).  a [M,K], w [N,K] CUDA fp16 or bf16."""
     assert a.dtype in (torch.float16, torch.bfloat16) and w.dtype == a.dtype and a.is_cuda and w.is_cuda
     a, w = a.contiguous(), w.contiguous()
     M, K = a.shape
     N = w.shape[0]
-    out = torch.empty((M // 4 if gap4 else M, N), dtype=torch.float32 if out_f32 else a.dtype, device=a.device)
+    if out is None:
+        out = torch.empty((M // 4 if gap4 else M, N), dtype=torch.float32 if out_f32 else a.dtype, device=a.device)
     _lib.check(_lib.lib().kws_gemm_h16(a.data_ptr(), w.data_ptr(), M, N, K, bias.data_ptr() if bias is not None else None,
                                        int(act), residual.data_ptr() if residual is not None else None, out.data_ptr(),
                                        int(out_f32), int(gap4), int(block_n), 0 if a.dtype == torch.float16 else 1,

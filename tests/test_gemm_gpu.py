@@ -18,6 +18,8 @@ def ref(a, w, bias, act, residual, gap4):
         y = torch.relu(y)
     elif act == 3:
         y = SELU_L * torch.where(y > 0, y, SELU_A * (torch.exp(y) - 1))
+    elif act == 4:
+        y = torch.sigmoid(y)
     if residual is not None:
         y = y + residual.float()
     if gap4:
@@ -40,6 +42,9 @@ CASES = [
     (300, 2048, 2048, 2, False, False, False, 256),   # forced block_n 256 (512 TMEM columns)
     (5, 96, 16, 1, False, False, False, 0),           # tiny M
     (70000, 96, 16, 1, False, False, False, 0),       # many tiles per CTA: exercises ring + TMEM phase wrap
+    (1024, 1152, 48, 4, False, False, False, 0),      # SE-expand-like: sigmoid, several n tiles of 64k columns
+    (4100, 672, 112, 1, False, False, False, 64),     # forced block_n 64, ragged M, TMA-store clipping
+    (999, 112, 672, 0, True, False, False, 48),       # forced narrow tiles (direct-store path with n_tiles > 1)
 ]
 
 
@@ -70,3 +75,19 @@ def test_gemm_no_bias_identity(kws_lib):
     out = gemm_h16(a, w, None, 0, None, True)
     torch.cuda.synchronize()
     assert torch.equal(out, a.float())
+
+
+def test_gemm_in_place_residual(kws_lib):
+    """The skip connection is applied in place (output buffer == residual buffer), as the embedding runtime does."""
+    from multilingual_kws_b200.model import gemm_h16
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 3000, 80, 480
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.2
+    x = torch.randn(M, N, device="cuda", generator=g).half()
+    want = ref(a, w, bias, 0, x, False)
+    buf = x.clone()
+    gemm_h16(a, w, bias, 0, buf, out=buf)
+    torch.cuda.synchronize()
+    assert bool(((buf.float() - want).abs() <= 2e-3 + 2 ** -10 * want.abs()).all())
