@@ -27,11 +27,17 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int stages, int s
   return L;
 }
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5: one MUFU op instead of EX2 + RCP (the result is rounded to 16 bits anyway)
 __device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == kActSwish) return __fdividef(x, 1.0f + __expf(-x));
+  if (act == kActSwish) { const float h = 0.5f * x; return fmaf(h, tanh_approx(h), h); }
   if (act == kActRelu) return fmaxf(x, 0.0f);
   if (act == kActSelu) return x > 0.0f ? 1.0507009873554805f * x : 1.7580993408473766f * (__expf(x) - 1.0f);
-  if (act == kActSigmoid) return __fdividef(1.0f, 1.0f + __expf(-x));
+  if (act == kActSigmoid) return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f);
   return x;
 }
 
@@ -116,7 +122,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiCtx& c, const uint32_t (
   }
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kGemmThreads, kMinBlocks)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmShape sh, const GemmEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -369,6 +376,7 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   const int num_kb = (K + kGemmBlockK - 1) / kGemmBlockK;
   const size_t budget = 220 * 1024;
   int stages = kGemmMaxStages;
+  if (num_kb <= 2 && sh.block_n <= 128) stages = 3;   // small-K layers: leaves room for two CTAs per SM
   while (stages > 2 && smem_layout(sh.block_n, stages, staging_rows).total + 1024 > budget) --stages;
   if (stages > num_kb + 2) stages = num_kb + 2;
   if (stages < 2) stages = 2;
@@ -387,14 +395,25 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   } else {
     tout = ta;   // unused
   }
-  static size_t configured = 0;
-  if (smem > configured) {
-    KWS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   const int tiles = sh.m_tiles * sh.n_tiles;
-  const int grid = tiles < sm_count ? tiles : sm_count;
-  gemm_tcgen05_kernel<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tout, sh, ep);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)sh.block_n) tmem_cols <<= 1;
+  // Memory/latency-bound shapes (small K, many tiles): two co-resident CTAs per SM hide each other's TMA, TMEM and
+  // store latencies.  Needs half the shared memory and at most 256 TMEM columns per CTA.
+  const bool two = smem <= 112 * 1024 && tmem_cols <= 256 && tiles >= 2 * sm_count;
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[two ? 1 : 0]) {
+    if (two) KWS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else KWS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[two ? 1 : 0] = smem;
+  }
+  if (two) {
+    const int grid = tiles < 2 * sm_count ? tiles : 2 * sm_count;
+    gemm_tcgen05_kernel<2><<<grid, kGemmThreads, smem, stream>>>(ta, tb, tout, sh, ep);
+  } else {
+    const int grid = tiles < sm_count ? tiles : sm_count;
+    gemm_tcgen05_kernel<1><<<grid, kGemmThreads, smem, stream>>>(ta, tb, tout, sh, ep);
+  }
   KWS_CUDA_CHECK(cudaGetLastError());
   return KWS_OK;
 }
