@@ -261,7 +261,7 @@ def run_ours(args, rank, local_rank, world):
             roof = dict(kernel=top, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
                         traffic=None, launches_per_step=a["launches"], avg_launch_ms=a["ms"] / a["launches"],
                         peak_source=peaks["source"],
-                        note="algorithmic activation bytes (read + write) of all launches of the kernel / sum of durations")
+                        note="algorithmic activation bytes (input read + gated output write) of all launches / sum of durations")
         roof["per_kernel_ms"] = {k: round(v["ms"], 4) for k, v in agg.items()}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload

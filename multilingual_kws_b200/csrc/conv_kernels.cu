@@ -73,143 +73,155 @@ stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, uint1
 }
 
 // ---------------------------------------------------------------- depthwise + SE
-// Two kernels per MBConv middle section (the inputs were just written by the expand GEMM and are L2-resident):
-//   dwpool_kernel   depthwise conv + BN + swish straight from / to global memory (no staging, small smem, so
-//                   several CTAs per SM hide the load latency) and the per-clip channel sums (global average pool);
-//   se_scale_kernel per group of clips: SE reduce FC + swish, SE expand FC + sigmoid, then the gated activation is
-//                   written in place as the next GEMM's A operand.
 constexpr int kDwThreads = 256;
 
-// thread -> (channel pair, pixel lane): PL lanes share one channel pair when C/2 < 256
-__host__ __device__ inline int dw_pixel_lanes(int C) { return (C >> 1) >= kDwThreads ? 1 : kDwThreads / (C >> 1); }
-
-template <int K, int S>
-__global__ void __launch_bounds__(kDwThreads, 2)
-dwpool_kernel(const uint16_t* __restrict__ x, int batch, DwseParams P, uint16_t* __restrict__ y,
-              float* __restrict__ pooled) {
-  extern __shared__ __align__(128) uint8_t smem_dw[];
-  float* s_part = reinterpret_cast<float*>(smem_dw);         // [2][PL][C] partial channel sums (PL > 1 only)
-  const int tid = threadIdx.x;
-  const int C = P.C, C2 = C >> 1, npix = P.Ho * P.Wo;
-  const size_t clip_words = (size_t)P.H * P.W * C2;
-  const int PL = dw_pixel_lanes(C);
-  const int cp0 = C2 >= kDwThreads ? tid : tid % C2;
-  const int pl = C2 >= kDwThreads ? 0 : tid / C2;
-  const bool active = pl < PL;
-  const uint32_t* x32 = reinterpret_cast<const uint32_t*>(x);
-  uint32_t* y32 = reinterpret_cast<uint32_t*>(y);
-
-  for (int cp = cp0; cp < C2; cp += kDwThreads) {             // one pass when C2 <= 256
-    float2 wreg[K * K];
-#pragma unroll
-    for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp);
-    const float2 bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp);
-    int buf = 0;
-    for (int clip = blockIdx.x; clip < batch; clip += gridDim.x) {
-      float sum0 = 0.0f, sum1 = 0.0f;
-      if (active) {
-        const uint32_t* in_g = x32 + (size_t)clip * clip_words + cp;
-        // Row strips with a K x K register window: the pixel lane `pl` owns output rows ho = pl, pl + PL, ...; along a
-        // row the window slides by S columns, so each output costs K*S loads instead of K*K.  Window columns live in
-        // slot (wo*S + kw) % K; the wo loop is unrolled by K so slots are compile-time.
-        for (int ho = pl; ho < P.Ho; ho += PL) {
-          const uint32_t* rowp[K];
-          bool row_ok[K];
-#pragma unroll
-          for (int kh = 0; kh < K; ++kh) {
-            const int r = ho * S + kh - P.pad_top;
-            row_ok[kh] = (r >= 0) && (r < P.H);
-            rowp[kh] = in_g + (size_t)(row_ok[kh] ? r : 0) * P.W * C2;
-          }
-          float2 win[K][K];
-          uint32_t* orow = y32 + ((size_t)clip * npix + (size_t)ho * P.Wo) * C2 + cp;
-          for (int wo_base = 0; wo_base < P.Wo; wo_base += K) {
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-              const int wo = wo_base + j;
-              if (wo < P.Wo) {
-#pragma unroll
-                for (int kw = 0; kw < K; ++kw) {
-                  if (kw >= K - S || wo == 0) {                 // new columns (all K of them for the first output)
-                    const int c = wo * S + kw - P.pad_left;
-                    const bool col_ok = (c >= 0) && (c < P.W);
-                    const int slot = (j * S + kw) % K;
-#pragma unroll
-                    for (int kh = 0; kh < K; ++kh) {
-                      if (!row_ok[kh]) continue;
-                      float2 v = make_float2(0.0f, 0.0f);
-                      if (col_ok) v = ptx::unpack_h2(__ldg(rowp[kh] + (size_t)c * C2), P.bf16);
-                      win[kh][slot] = v;
-                    }
-                  }
-                }
-                float a0 = bias.x, a1 = bias.y;
-#pragma unroll
-                for (int kh = 0; kh < K; ++kh) {
-                  if (!row_ok[kh]) continue;                    // padded rows contribute nothing
-#pragma unroll
-                  for (int kw = 0; kw < K; ++kw) {
-                    const int slot = (j * S + kw) % K;
-                    a0 = fmaf(win[kh][slot].x, wreg[kh * K + kw].x, a0);
-                    a1 = fmaf(win[kh][slot].y, wreg[kh * K + kw].y, a1);
-                  }
-                }
-                a0 = swish(a0);
-                a1 = swish(a1);
-                sum0 += a0;
-                sum1 += a1;
-                orow[(size_t)wo * C2] = ptx::pack_h2(a0, a1, P.bf16);
-              }
-            }
-          }
-        }
-      }
-      if (PL == 1) {
-        if (active) *reinterpret_cast<float2*>(pooled + (size_t)clip * C + 2 * cp) = make_float2(sum0, sum1);
-      } else {
-        // fixed-order reduce over the pixel lanes (deterministic); double-buffered so one barrier per clip suffices
-        float* part = s_part + (size_t)buf * PL * C;
-        if (active) *reinterpret_cast<float2*>(part + (size_t)pl * C + 2 * cp) = make_float2(sum0, sum1);
-        __syncthreads();
-        if (tid < C) {
-          float a = 0.0f;
-          for (int q = 0; q < PL; ++q) a += part[q * C + tid];
-          pooled[(size_t)clip * C + tid] = a;
-        }
-        buf ^= 1;
-      }
-    }
-  }
-}
-
-struct SeSmem {
-  uint32_t s_off, red_off, total;
+struct DwSmem {
+  uint32_t in_bytes, out_off, pooled_off, part_off, s_off, red_off, bar_off, total;
+  int PL;   // pixel lanes per channel pair
 };
-__host__ __device__ inline SeSmem se_smem(const DwseParams& P, int G) {
-  SeSmem L;
-  L.s_off = (uint32_t)G * P.C * 4;                                              // after s_pool [G][C]
-  L.red_off = (L.s_off + (uint32_t)G * P.se * 4 + 15) & ~15u;                   // [se][8 warps][4 clips] FC1 partials
-  L.total = L.red_off + (uint32_t)P.se * (kDwThreads / 32) * 4 * 4;
+__host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
+  DwSmem L;
+  const int C2 = P.C >> 1;
+  L.PL = C2 >= kDwThreads ? 1 : kDwThreads / C2;
+  L.in_bytes = (uint32_t)G * P.H * P.W * P.C * 2;
+  L.out_off = (L.in_bytes + 127) & ~127u;
+  L.pooled_off = L.out_off + (((uint32_t)G * P.Ho * P.Wo * P.C * 2 + 127) & ~127u);
+  L.part_off = L.pooled_off + (uint32_t)G * P.C * 4;                       // [PL][G][C] partial channel sums
+  L.s_off = L.part_off + (L.PL > 1 ? (uint32_t)L.PL * G * P.C * 4 : 0u);
+  L.red_off = (L.s_off + (uint32_t)G * P.se * 4 + 15) & ~15u;                            // [se][8 warps][4 clips] FC1 partials
+  L.bar_off = (L.red_off + (uint32_t)P.se * (kDwThreads / 32) * 4 * 4 + 15) & ~15u;
+  L.total = L.bar_off + 16;
   return L;
 }
 
+template <int K, int S>
 __global__ void __launch_bounds__(kDwThreads)
-se_scale_kernel(const float* __restrict__ pooled, int batch, int G, DwseParams P, uint16_t* __restrict__ y) {
+dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint16_t* __restrict__ y) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const SeSmem L = se_smem(P, G);
-  float* s_pool = reinterpret_cast<float*>(smem);                               // [G][C] sums, later gates
-  float* s_se = reinterpret_cast<float*>(smem + L.s_off);                      // [G][se]
-  float* s_red = reinterpret_cast<float*>(smem + L.red_off);                   // [se][warps][4]
+  const DwSmem L = dw_smem(P, G);
+  const uint32_t* s_in = reinterpret_cast<const uint32_t*>(smem);              // bf16x2 words, [G][H][W][C/2]
+  uint32_t* s_out = reinterpret_cast<uint32_t*>(smem + L.out_off);            // bf16x2, [G][Ho*Wo][C/2]
+  float* s_pool = reinterpret_cast<float*>(smem + L.pooled_off);              // [G][C] sums, later gates
+  float* s_part = reinterpret_cast<float*>(smem + L.part_off);                // [PL][G][C] (deterministic pool reduce)
+  float* s_se = reinterpret_cast<float*>(smem + L.s_off);                     // [G][se]
+  float* s_red = reinterpret_cast<float*>(smem + L.red_off);                  // [se][warps][4]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int C = P.C, npix = P.Ho * P.Wo;
+  const int C = P.C, C2 = C >> 1, npix = P.Ho * P.Wo;
+  const int clip_words = P.H * P.W * C2;
   const float inv_npix = 1.0f / (float)npix;
+
+  if (tid == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  // thread -> (channel pair, pixel lane)
+  const int PL = L.PL;
+  const int cp0 = C2 >= kDwThreads ? tid : tid % C2;
+  const int pl = C2 >= kDwThreads ? 0 : tid / C2;
+  const bool active = pl < PL;
+  uint32_t parity = 0;
+
   const int n_groups = (batch + G - 1) / G;
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const int g0 = grp * G;
     const int gn = min(G, batch - g0);
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)gn * clip_words * 4;
+      ptx::mbar_expect_tx(bar, bytes);
+      ptx::tma_bulk_g2s(smem, x + (size_t)g0 * clip_words * 2, bytes, bar);
+    }
+    ptx::mbar_wait(bar, parity);
+    parity ^= 1;
     __syncthreads();
-    for (int i = tid; i < gn * C; i += kDwThreads) s_pool[i] = pooled[(size_t)g0 * C + i];
+
+    // ---- depthwise conv + BN + swish -> s_out (bf16), channel sums -> s_pool
+    if (active) {
+      for (int cp = cp0; cp < C2; cp += kDwThreads) {
+        float2 wreg[K * K];
+#pragma unroll
+        for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp);
+        const float2 bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp);
+        for (int g = 0; g < gn; ++g) {
+          const uint32_t* in_g = s_in + (size_t)g * clip_words + cp;
+          float sum0 = 0.0f, sum1 = 0.0f;
+          // Row strips with a K x K register window: the pixel lane `pl` owns output rows ho = pl, pl + PL, ...;
+          // along a row the window slides by S columns, so each output costs K*S shared-memory loads instead of K*K.
+          // Window columns live in slot (wo*S + kw) % K; the wo loop is unrolled by K so slots are compile-time.
+          for (int ho = pl; ho < P.Ho; ho += PL) {
+            const uint32_t* rowp[K];
+            bool row_ok[K];
+#pragma unroll
+            for (int kh = 0; kh < K; ++kh) {
+              const int r = ho * S + kh - P.pad_top;
+              row_ok[kh] = (r >= 0) && (r < P.H);
+              rowp[kh] = in_g + (size_t)(row_ok[kh] ? r : 0) * P.W * C2;
+            }
+            float2 win[K][K];
+            uint32_t* orow = s_out + ((size_t)g * npix + (size_t)ho * P.Wo) * C2 + cp;
+            for (int wo_base = 0; wo_base < P.Wo; wo_base += K) {
+#pragma unroll
+              for (int j = 0; j < K; ++j) {
+                const int wo = wo_base + j;
+                if (wo < P.Wo) {
+#pragma unroll
+                  for (int kw = 0; kw < K; ++kw) {
+                    if (kw >= K - S || wo == 0) {                 // new columns (all K of them for the first output)
+                      const int c = wo * S + kw - P.pad_left;
+                      const bool col_ok = (c >= 0) && (c < P.W);
+                      constexpr int dummy = 0; (void)dummy;
+                      const int slot = (j * S + kw) % K;
+#pragma unroll
+                      for (int kh = 0; kh < K; ++kh) {
+                        if (!row_ok[kh]) continue;
+                        float2 v = make_float2(0.0f, 0.0f);
+                        if (col_ok) v = ptx::unpack_h2(rowp[kh][c * C2], P.bf16);
+                        win[kh][slot] = v;
+                      }
+                    }
+                  }
+                  float a0 = bias.x, a1 = bias.y;
+#pragma unroll
+                  for (int kh = 0; kh < K; ++kh) {
+                    if (!row_ok[kh]) continue;                    // padded rows contribute nothing (tiny late maps: most rows)
+#pragma unroll
+                    for (int kw = 0; kw < K; ++kw) {
+                      const int slot = (j * S + kw) % K;
+                      a0 = fmaf(win[kh][slot].x, wreg[kh * K + kw].x, a0);
+                      a1 = fmaf(win[kh][slot].y, wreg[kh * K + kw].y, a1);
+                    }
+                  }
+                  a0 = swish(a0);
+                  a1 = swish(a1);
+                  sum0 += a0;
+                  sum1 += a1;
+                  orow[(size_t)wo * C2] = ptx::pack_h2(a0, a1, P.bf16);
+                }
+              }
+            }
+          }
+          if (PL == 1) {
+            s_pool[g * C + 2 * cp] = sum0;
+            s_pool[g * C + 2 * cp + 1] = sum1;
+          } else {
+            s_part[(pl * gn + g) * C + 2 * cp] = sum0;
+            s_part[(pl * gn + g) * C + 2 * cp + 1] = sum1;
+          }
+        }
+      }
+    }
     __syncthreads();
+    if (PL > 1) {                     // fixed-order sum over pixel lanes: results do not depend on scheduling
+      for (int i = tid; i < gn * C; i += kDwThreads) {
+        float a = 0.0f;
+        for (int q = 0; q < PL; ++q) a += s_part[q * gn * C + i];
+        s_pool[i] = a;
+      }
+      __syncthreads();
+    }
 
     // ---- SE reduce: s[g][j] = swish(b1[j] + mean_g . w1[j][:]).  Every thread owns channels c = tid + 256 i and
     // streams its slice of every weight row (coalesced, independent loads -> deep memory-level parallelism);
@@ -281,31 +293,33 @@ se_scale_kernel(const float* __restrict__ pooled, int batch, int G, DwseParams P
     }
     __syncthreads();
 
-    // ---- scale in place: 16-byte vectors (8 channels), coalesced; no div/mod in the loop
+    // ---- scale and store: 16-byte vectors (8 channels), coalesced; no div/mod in the loop
     {
       const int C8 = C >> 3;                                  // uint4 vectors per pixel
       const int vec_per_clip = npix * C8;
       const int step = kDwThreads % C8;
       for (int g = 0; g < gn; ++g) {
+        const uint4* src = reinterpret_cast<const uint4*>(s_out) + (size_t)g * vec_per_clip;
         uint4* dst = reinterpret_cast<uint4*>(y) + ((size_t)(g0 + g) * vec_per_clip);
         const float* gate = s_pool + g * C;
         int c8 = tid % C8;
         for (int i = tid; i < vec_per_clip; i += kDwThreads) {
-          const uint4 v = dst[i];
+          const uint4 v = src[i];
           const float4 g0v = *reinterpret_cast<const float4*>(gate + 8 * c8);
           const float4 g1v = *reinterpret_cast<const float4*>(gate + 8 * c8 + 4);
-          float2 xv;
+          float2 x;
           uint4 o;
-          xv = ptx::unpack_h2(v.x, P.bf16); o.x = ptx::pack_h2(xv.x * g0v.x, xv.y * g0v.y, P.bf16);
-          xv = ptx::unpack_h2(v.y, P.bf16); o.y = ptx::pack_h2(xv.x * g0v.z, xv.y * g0v.w, P.bf16);
-          xv = ptx::unpack_h2(v.z, P.bf16); o.z = ptx::pack_h2(xv.x * g1v.x, xv.y * g1v.y, P.bf16);
-          xv = ptx::unpack_h2(v.w, P.bf16); o.w = ptx::pack_h2(xv.x * g1v.z, xv.y * g1v.w, P.bf16);
+          x = ptx::unpack_h2(v.x, P.bf16); o.x = ptx::pack_h2(x.x * g0v.x, x.y * g0v.y, P.bf16);
+          x = ptx::unpack_h2(v.y, P.bf16); o.y = ptx::pack_h2(x.x * g0v.z, x.y * g0v.w, P.bf16);
+          x = ptx::unpack_h2(v.z, P.bf16); o.z = ptx::pack_h2(x.x * g1v.x, x.y * g1v.y, P.bf16);
+          x = ptx::unpack_h2(v.w, P.bf16); o.w = ptx::pack_h2(x.x * g1v.z, x.y * g1v.w, P.bf16);
           dst[i] = o;
           c8 += step;
           if (c8 >= C8) c8 -= C8;
         }
       }
     }
+    __syncthreads();
   }
 }
 
@@ -321,33 +335,33 @@ int launch_stem(const float* d_feats, int batch, const StemParams& P, void* d_ou
   return KWS_OK;
 }
 
-int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, float* d_pooled, int sm_count,
+int dwse_pick_group(const DwseParams& P, int max_smem, int batch, int sm_count) {
+  const int cands[5] = {16, 8, 4, 2, 1};
+  int fit = 0;
+  for (int i = 0; i < 5 && !fit; ++i)
+    if ((int)dw_smem(P, cands[i]).total <= 100 * 1024) fit = cands[i];
+  for (int i = 0; i < 5 && !fit; ++i)
+    if ((int)dw_smem(P, cands[i]).total <= max_smem) fit = cands[i];
+  if (!fit) return 0;
+  while (fit > 1 && (batch + fit - 1) / fit < sm_count) fit >>= 1;       // at least one group per SM
+  return fit;
+}
+
+int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int G, int sm_count,
                 cudaStream_t st) {
   if (batch == 0) return KWS_OK;
+  KWS_REQUIRE(G >= 1, "dwse: layer does not fit shared memory");
   KWS_REQUIRE(P.C % 8 == 0, "dwse: channels must be a multiple of 8");
   KWS_REQUIRE((P.K == 3 || P.K == 5) && (P.S == 1 || P.S == 2), "dwse: unsupported kernel %d / stride %d", P.K, P.S);
-  KWS_REQUIRE(d_pooled != nullptr, "dwse: pooled scratch is NULL");
-  // 1. depthwise + BN + swish + channel sums
-  {
-    void (*kern)(const uint16_t*, int, DwseParams, uint16_t*, float*) =
-        P.K == 3 ? (P.S == 1 ? dwpool_kernel<3, 1> : dwpool_kernel<3, 2>)
-                 : (P.S == 1 ? dwpool_kernel<5, 1> : dwpool_kernel<5, 2>);
-    const int PL = dw_pixel_lanes(P.C);
-    const size_t smem = PL > 1 ? (size_t)2 * PL * P.C * 4 : 0;
-    const int grid = batch < sm_count * 4 ? batch : sm_count * 4;
-    kern<<<grid, kDwThreads, smem, st>>>(static_cast<const uint16_t*>(d_x), batch, P, static_cast<uint16_t*>(d_y), d_pooled);
-    KWS_CUDA_CHECK(cudaGetLastError());
-  }
-  // 2. squeeze-excite gates + in-place scaling; clips per CTA chosen so every SM gets a group
-  {
-    int G = 8;
-    while (G > 1 && (batch + G - 1) / G < 2 * sm_count) G >>= 1;
-    const size_t smem = se_smem(P, G).total;
-    const int n_groups = (batch + G - 1) / G;
-    const int grid = n_groups < sm_count * 4 ? n_groups : sm_count * 4;
-    se_scale_kernel<<<grid, kDwThreads, smem, st>>>(d_pooled, batch, G, P, static_cast<uint16_t*>(d_y));
-    KWS_CUDA_CHECK(cudaGetLastError());
-  }
+  const size_t smem = dw_smem(P, G).total;
+  void (*kern)(const uint16_t*, int, int, DwseParams, uint16_t*) =
+      P.K == 3 ? (P.S == 1 ? dwse_kernel<3, 1> : dwse_kernel<3, 2>) : (P.S == 1 ? dwse_kernel<5, 1> : dwse_kernel<5, 2>);
+  KWS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_groups = (batch + G - 1) / G;
+  const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+  const int grid = n_groups < sm_count * per_sm ? n_groups : sm_count * per_sm;
+  kern<<<grid, kDwThreads, smem, st>>>(static_cast<const uint16_t*>(d_x), batch, G, P, static_cast<uint16_t*>(d_y));
+  KWS_CUDA_CHECK(cudaGetLastError());
   return KWS_OK;
 }
 

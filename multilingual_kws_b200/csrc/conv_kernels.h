@@ -25,9 +25,9 @@ struct DwseParams {
 };
 
 int launch_stem(const float* d_feats, int batch, const StemParams& P, void* d_out, int sm_count, cudaStream_t st);
-// depthwise + BN + swish + SE for `batch` clips: two launches (dwpool_kernel, se_scale_kernel);
-// d_pooled: scratch of batch * C floats.
-int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, float* d_pooled, int sm_count,
+// clips per CTA iteration: fits shared memory (<= 100 KB when possible) and leaves >= 2 groups per SM
+int dwse_pick_group(const DwseParams& P, int max_smem, int batch, int sm_count);
+int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int G, int sm_count,
                 cudaStream_t st);
 
 }  // namespace kws

@@ -85,6 +85,7 @@ struct Op {
   const float* bias = nullptr;
   StemParams stem{};
   DwseParams dw{};
+  int dw_group = 1;
   size_t out_elems_per_clip = 0;
   double flops_per_clip = 0;           // 2 * MACs
   double bytes_per_clip = 0;           // algorithmic: activation read + write (weights excluded)
@@ -109,7 +110,6 @@ struct kws_embed {
   // one) have up to 96 KB of activations per clip and are walked in small chunks so they stay L2-resident; "late"
   // ops have <= 37 KB per clip and run over large chunks so GEMM tiles / depthwise groups fill the 148 SMs.
   int split_op = 0;                    // first late op
-  size_t max_dw_channels = 0;          // pooled scratch = clips per pass * this many floats
   size_t buf_elems[2][3] = {{0, 0, 0}, {0, 0, 0}};   // [segment][X, E, D] per clip, 16-bit elements
   int sm_count = 0, max_smem = 0;
   int chunk = 256;                     // early-segment clips per pass
@@ -294,7 +294,8 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
         P.w_se2 = B.vec(std::vector<float>(w2->data, w2->data + (size_t)se * cexp));
         P.b_se2 = B.vec(std::vector<float>(b2->data, b2->data + cexp));
         CK(P.w_dw && P.b_dw && P.w_se1 && P.b_se1 && P.w_se2 && P.b_se2);
-        if ((size_t)cexp > m->max_dw_channels) m->max_dw_channels = (size_t)cexp;
+        op.dw_group = dwse_pick_group(P, m->max_smem, 1 << 20, m->sm_count);
+        if (op.dw_group < 1) { B.err = "depthwise layer " + n + " does not fit shared memory"; return fail(KWS_ERR_UNSUPPORTED); }
         macs += (double)P.Ho * P.Wo * cexp * k * k + 2.0 * cexp * se;
         h = P.Ho; w = P.Wo;
         op.out_elems_per_clip = (size_t)h * w * cexp;
@@ -466,12 +467,7 @@ extern "C" int kws_embed_launches(const kws_embed_t* m, int batch) {
   if (!m || batch <= 0) return 0;
   const int ce = batch < m->chunk ? batch : m->chunk, cl = batch < m->chunk_late ? batch : m->chunk_late;
   const int n_ops = (int)m->ops.size();
-  int launches = 0;
-  for (int i = 0; i < n_ops; ++i) {
-    const int per = m->ops[i].kind == kOpDwse ? 2 : 1;        // depthwise+pool, then SE+scale
-    launches += per * (i < m->split_op ? (batch + ce - 1) / ce : (batch + cl - 1) / cl);
-  }
-  return launches;
+  return ((batch + ce - 1) / ce) * m->split_op + ((batch + cl - 1) / cl) * (n_ops - m->split_op);
 }
 
 extern "C" int kws_embed_set_graph(kws_embed_t* m, int enable) {
@@ -486,8 +482,7 @@ extern "C" size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch) {
   const size_t cl = (size_t)(batch < m->chunk_late ? batch : m->chunk_late);
   const size_t early = (m->buf_elems[0][0] + m->buf_elems[0][1] + m->buf_elems[0][2]) * ce;
   const size_t late = m->buf_elems[1][0] * (size_t)batch + (m->buf_elems[1][1] + m->buf_elems[1][2]) * cl;
-  const size_t pooled = (ce > cl ? ce : cl) * m->max_dw_channels * sizeof(float);
-  return round_up((early + late) * 2, 256) + pooled + 2048;
+  return (early + late) * 2 + 2048;
 }
 
 // tap_op >= 0: additionally copy the output of op `tap_op` (bf16 NHWC, or fp32 for the last op) to d_tap.
@@ -552,8 +547,6 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
   uint16_t* H = early[2] + m->buf_elems[0][2] * chunk_seg[0];
   uint16_t* late_e = H + m->buf_elems[1][0] * (size_t)batch;
   uint16_t* late_d = late_e + m->buf_elems[1][1] * chunk_seg[1];
-  float* pooled = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d_workspace) +
-      round_up((size_t)((late_d + m->buf_elems[1][2] * chunk_seg[1]) - base) * 2, 256));
 
   std::vector<cudaEvent_t> evs;
   size_t ev_i = 0;
@@ -588,7 +581,8 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
         if (op.kind == kOpStem) {
           rc = launch_stem(d_feats + (size_t)b0 * m->H * m->W, nb, op.stem, out_ptr, m->sm_count, st);
         } else if (op.kind == kOpDwse) {
-          rc = launch_dwse(bufs[op.in_buf], nb, op.dw, out_ptr, pooled, m->sm_count, st);
+          rc = launch_dwse(bufs[op.in_buf], nb, op.dw, out_ptr, dwse_pick_group(op.dw, m->max_smem, nb, m->sm_count),
+                           m->sm_count, st);
         } else {
           GemmEpilogue ep;
           ep.bias = op.bias;

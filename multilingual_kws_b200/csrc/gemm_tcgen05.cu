@@ -376,7 +376,7 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   const int num_kb = (K + kGemmBlockK - 1) / kGemmBlockK;
   const size_t budget = 220 * 1024;
   int stages = kGemmMaxStages;
-  if (num_kb <= 2 && sh.block_n <= 128) stages = 3;   // small-K layers: leaves room for two CTAs per SM
+  if (num_kb <= 2 && sh.block_n <= 128) stages = num_kb == 1 ? 2 : 3;   // small-K layers: leaves room for two CTAs per SM
   while (stages > 2 && smem_layout(sh.block_n, stages, staging_rows).total + 1024 > budget) --stages;
   if (stages > num_kb + 2) stages = num_kb + 2;
   if (stages < 2) stages = 2;

@@ -5,7 +5,7 @@ import numpy as np, torch
 from multilingual_kws_b200.model import gemm_h16
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-shapes = [("b1a_proj", 500, 16, 32, 0), ("b2a_expand", 500, 96, 16, 1), ("b2a_proj", 130, 24, 96, 0), ("b2b_expand", 130, 144, 24, 1),
+shapes = [("packed4_b2a_expand", 125, 384, 64, 1), ("k64_n96", 500, 96, 64, 1), ("k16_n16", 500, 16, 16, 0), ("b1a_proj", 500, 16, 32, 0), ("b2a_expand", 500, 96, 16, 1), ("b2a_proj", 130, 24, 96, 0), ("b2b_expand", 130, 144, 24, 1),
           ("b3b_expand", 35, 240, 40, 1), ("b4b_expand", 12, 480, 80, 1), ("b5b_expand", 12, 672, 112, 1), ("b5b_proj", 12, 112, 672, 0),
           ("b6b_expand", 4, 1152, 192, 1), ("b6b_proj", 4, 192, 1152, 0), ("b7a_proj", 4, 320, 1152, 0), ("top", 4, 1280, 320, 1),
           ("dense", 1, 2048, 1280, 2), ("dense_1", 1, 2048, 2048, 2), ("dense_2", 1, 1024, 2048, 3)]
