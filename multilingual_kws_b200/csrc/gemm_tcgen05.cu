@@ -10,16 +10,15 @@ namespace kws {
 
 namespace {
 
-constexpr uint32_t kABytes = kGemmBlockM * kGemmBlockK * 2;   // 16 KiB per stage
 
 struct SmemLayout {
   uint32_t stage_bytes, staging_off, staging_bytes, bar_off, bias_off, total;
 };
 // staging: the output tile in TMA-store layout: ceil(block_n / 64) boxes of [rows_box][64] 16-bit, SWIZZLE_128B
-__host__ __device__ inline SmemLayout smem_layout(int block_n, int stages, int staging_rows) {
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int block_k, int stages, int staging_rows) {
   SmemLayout L;
-  L.stage_bytes = kABytes + (uint32_t)block_n * kGemmBlockK * 2;
-  L.staging_off = L.stage_bytes * stages;                              // multiple of 1024
+  L.stage_bytes = (uint32_t)(kGemmBlockM + block_n) * block_k * 2;     // A tile then W tile, both multiples of 512 B
+  L.staging_off = (L.stage_bytes * stages + 1023) & ~1023u;
   L.staging_bytes = (uint32_t)((block_n + 63) / 64) * staging_rows * 128;
   L.bar_off = L.staging_off + L.staging_bytes;
   L.bias_off = L.bar_off + 8 * (2 * kGemmMaxStages + 4) + 16;          // float s_bias[2][256]
@@ -129,7 +128,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int staging_rows = sh.tma_store ? (ep.gap4 ? kGemmBlockM / 4 : kGemmBlockM) : 0;
-  const SmemLayout L = smem_layout(sh.block_n, sh.stages, staging_rows);
+  const SmemLayout L = smem_layout(sh.block_n, sh.block_k, sh.stages, staging_rows);
+  const uint32_t a_bytes = (uint32_t)kGemmBlockM * sh.block_k * 2;
   uint8_t* staging = sh.tma_store ? smem + L.staging_off : nullptr;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + kGemmMaxStages;
@@ -140,7 +140,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int block_n = sh.block_n, stages = sh.stages;
-  const int num_kb = (sh.K + kGemmBlockK - 1) / kGemmBlockK;
+  const int num_kb = (sh.K + sh.block_k - 1) / sh.block_k;
   const int k16_total = (sh.K + 15) / 16;
   const int total_tiles = sh.m_tiles * sh.n_tiles;
   uint32_t tmem_cols = 32;
@@ -182,8 +182,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ptx::mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * L.stage_bytes;
           ptx::mbar_expect_tx(full_bar + stage, L.stage_bytes);
-          ptx::tma_load_2d(&tmap_a, full_bar + stage, sa, kb * kGemmBlockK, m_t * kGemmBlockM);
-          ptx::tma_load_2d(&tmap_b, full_bar + stage, sa + kABytes, kb * kGemmBlockK, n_t * block_n);
+          ptx::tma_load_2d(&tmap_a, full_bar + stage, sa, kb * sh.block_k, m_t * kGemmBlockM);
+          ptx::tma_load_2d(&tmap_b, full_bar + stage, sa + a_bytes, kb * sh.block_k, n_t * block_n);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -205,9 +205,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ptx::mbar_wait(full_bar + stage, phase);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * L.stage_bytes);
-          const uint64_t a_desc = ptx::umma_desc_kmajor_sw128(sa);
-          const uint64_t b_desc = ptx::umma_desc_kmajor_sw128(sa + kABytes);
-          const int ksteps = min(4, k16_total - kb * 4);
+          const uint64_t a_desc = ptx::umma_desc_kmajor(sa, (uint32_t)sh.block_k * 2);
+          const uint64_t b_desc = ptx::umma_desc_kmajor(sa + a_bytes, (uint32_t)sh.block_k * 2);
+          const int k16_per_kb = sh.block_k >> 4;
+          const int ksteps = min(k16_per_kb, k16_total - kb * k16_per_kb);
           for (int k = 0; k < ksteps; ++k)   // +32 B along K inside the 128 B swizzle atom = +2 in the (addr >> 4) field
             ptx::tc_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
           ptx::tc_commit(empty_bar + stage);              // smem slot free once these MMAs retire
@@ -308,6 +309,8 @@ EncodeTiledFn get_encode_fn() {
 // Few-tile problems (late layers, dense tower) get narrow tiles so all SMs work; big-M problems get the widest
 // tile with little column padding.  With several n-tiles the TMA-store boxes (64 columns) must not cross into
 // the neighbouring tile, so block_n is then a multiple of 64.
+int pick_block_k(int K) { return K <= 16 ? 16 : (K <= 32 ? 32 : 64); }
+
 int pick_block_n(int N, int K, int m_tiles, int sm_count, bool tma_store) {
   const int num_kb = (K + kGemmBlockK - 1) / kGemmBlockK;
   int best = 16;
@@ -331,7 +334,8 @@ int pick_block_n(int N, int K, int m_tiles, int sm_count, bool tma_store) {
 
 }  // namespace
 
-int make_tmap_h16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bf16) {
+int make_tmap_h16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bf16,
+                  uint32_t box_cols) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is unavailable (CUDA driver too old or no device)");
@@ -342,11 +346,14 @@ int make_tmap_h16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t co
   KWS_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box rows %u out of range", box_rows);
   const cuuint64_t gdim[2] = {cols, rows};
   const cuuint64_t gstride[1] = {cols * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kGemmBlockK, box_rows};
+  KWS_REQUIRE(box_cols == 16 || box_cols == 32 || box_cols == 64, "tensor map: box columns must be 16, 32 or 64");
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, box_rows};
+  const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu box_rows %u)", (int)r,
               (unsigned long long)rows, (unsigned long long)cols, box_rows);
@@ -373,21 +380,25 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   sh.n_tiles = (N + sh.block_n - 1) / sh.block_n;
   if (sh.tma_store && sh.n_tiles > 1 && (sh.block_n & 63)) sh.tma_store = 0;   // forced odd tile width: direct stores
   const int staging_rows = sh.tma_store ? (ep.gap4 ? kGemmBlockM / 4 : kGemmBlockM) : 0;
-  const int num_kb = (K + kGemmBlockK - 1) / kGemmBlockK;
-  const size_t budget = 220 * 1024;
+  sh.block_k = pick_block_k(K);
+  const int num_kb = (K + sh.block_k - 1) / sh.block_k;
+  const int tiles_per_cta = (sh.m_tiles * sh.n_tiles + sm_count - 1) / sm_count;
+  // Stage count = how many k-blocks (for single-k-block layers: how many TILES) may be in flight per CTA.  Memory-
+  // bound small-K layers want as many as fit in ~half the SM's shared memory (so two CTAs co-reside).
+  const size_t budget = (num_kb <= 2 && sh.block_n <= 128) ? 110 * 1024 : 220 * 1024;
   int stages = kGemmMaxStages;
-  if (num_kb <= 2 && sh.block_n <= 128) stages = num_kb == 1 ? 2 : 3;   // small-K layers: leaves room for two CTAs per SM
-  while (stages > 2 && smem_layout(sh.block_n, stages, staging_rows).total + 1024 > budget) --stages;
-  if (stages > num_kb + 2) stages = num_kb + 2;
+  while (stages > 2 && smem_layout(sh.block_n, sh.block_k, stages, staging_rows).total + 1024 > budget) --stages;
+  const int useful = num_kb * (tiles_per_cta < 8 ? tiles_per_cta : 8) + 1;
+  if (stages > useful) stages = useful;
   if (stages < 2) stages = 2;
   sh.stages = stages;
-  const size_t smem = smem_layout(sh.block_n, sh.stages, staging_rows).total + 1024;
+  const size_t smem = smem_layout(sh.block_n, sh.block_k, sh.stages, staging_rows).total + 1024;
   KWS_REQUIRE(smem <= 227 * 1024, "gemm: tile configuration does not fit shared memory");
 
   CUtensorMap ta, tb, tout;
-  int rc = make_tmap_h16(&ta, a, (uint64_t)M, (uint64_t)K, kGemmBlockM, ep.bf16);
+  int rc = make_tmap_h16(&ta, a, (uint64_t)M, (uint64_t)K, kGemmBlockM, ep.bf16, (uint32_t)sh.block_k);
   if (rc != KWS_OK) return rc;
-  rc = make_tmap_h16(&tb, w, (uint64_t)N, (uint64_t)K, (uint32_t)sh.block_n, ep.bf16);
+  rc = make_tmap_h16(&tb, w, (uint64_t)N, (uint64_t)K, (uint32_t)sh.block_n, ep.bf16, (uint32_t)sh.block_k);
   if (rc != KWS_OK) return rc;
   if (sh.tma_store) {
     rc = make_tmap_h16(&tout, ep.out, (uint64_t)(ep.gap4 ? M / 4 : M), (uint64_t)N, (uint32_t)staging_rows, ep.bf16);

@@ -22,9 +22,9 @@
 namespace kws {
 
 constexpr int kGemmBlockM = 128;
-constexpr int kGemmBlockK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B atom row
+constexpr int kGemmBlockK = 64;           // widest k-block: 64 x 16-bit = 128 B = one SWIZZLE_128B atom row
 constexpr int kGemmThreads = 320;         // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int kGemmMaxStages = 8;
+constexpr int kGemmMaxStages = 12;
 
 enum GemmAct : int { kActNone = 0, kActSwish = 1, kActRelu = 2, kActSelu = 3, kActSigmoid = 4 };
 
@@ -43,6 +43,8 @@ struct GemmShape {
   int M, N, K;
   int block_n;                       // multiple of 16, <= 256
   int stages;
+  int block_k;                       // 16 / 32 / 64 elements per k-block = SWIZZLE_32B / 64B / 128B tiles: small-K layers
+                                     // get narrow tiles, so many more of them fit in flight (memory-level parallelism)
   int m_tiles, n_tiles;
   int tma_store;                     // 1: epilogue stages the tile in swizzled smem and writes it with TMA stores
 };
@@ -53,6 +55,7 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
              cudaStream_t stream);
 
 // Host: 2-D 16-bit tensor map [rows, cols] (cols contiguous), box = {64, box_rows}, 128B swizzle, zero OOB fill.
-int make_tmap_h16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bf16);
+int make_tmap_h16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bf16,
+                  uint32_t box_cols = 64);
 
 }  // namespace kws

@@ -119,6 +119,14 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   return ((uint64_t)hi << 32) | lo;
 }
+// Same for a tile whose rows are row_bytes = 32 / 64 / 128 B wide (SWIZZLE_32B / 64B / 128B; layout codes 6 / 4 / 2):
+// SBO = 8 rows * row_bytes.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t row_bytes) {
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a format [7,10), b format [10,13),
 // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
 // fmt: 0 = F16, 1 = BF16 (F16F32Format) for both A and B.
