@@ -95,7 +95,7 @@ __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
 }
 
 template <int K, int S>
-__global__ void __launch_bounds__(kDwThreads)
+__global__ void __launch_bounds__(kDwThreads, 2)
 dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint16_t* __restrict__ y) {
   extern __shared__ __align__(128) uint8_t smem[];
   const DwSmem L = dw_smem(P, G);
@@ -134,6 +134,14 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
       ptx::mbar_expect_tx(bar, bytes);
       ptx::tma_bulk_g2s(smem, x + (size_t)g0 * clip_words * 2, bytes, bar);
     }
+    // first pass's depthwise weights: issued before the TMA wait so both latencies overlap
+    float2 wreg[K * K];
+    float2 bias = make_float2(0.0f, 0.0f);
+    if (active) {
+#pragma unroll
+      for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp0);
+      bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp0);
+    }
     ptx::mbar_wait(bar, parity);
     parity ^= 1;
     __syncthreads();
@@ -141,10 +149,11 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
     // ---- depthwise conv + BN + swish -> s_out (bf16), channel sums -> s_pool
     if (active) {
       for (int cp = cp0; cp < C2; cp += kDwThreads) {
-        float2 wreg[K * K];
+        if (cp != cp0) {
 #pragma unroll
-        for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp);
-        const float2 bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp);
+          for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp);
+          bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp);
+        }
         for (int g = 0; g < gn; ++g) {
           const uint32_t* in_g = s_in + (size_t)g * clip_words + cp;
           float sum0 = 0.0f, sum1 = 0.0f;
@@ -187,12 +196,15 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
 #pragma unroll
                   for (int kh = 0; kh < K; ++kh) {
                     if (!row_ok[kh]) continue;                    // padded rows contribute nothing (tiny late maps: most rows)
+                    float r0 = 0.0f, r1 = 0.0f;                   // per-row partials: K-deep instead of K*K-deep FMA chains
 #pragma unroll
                     for (int kw = 0; kw < K; ++kw) {
                       const int slot = (j * S + kw) % K;
-                      a0 = fmaf(win[kh][slot].x, wreg[kh * K + kw].x, a0);
-                      a1 = fmaf(win[kh][slot].y, wreg[kh * K + kw].y, a1);
+                      r0 = fmaf(win[kh][slot].x, wreg[kh * K + kw].x, r0);
+                      r1 = fmaf(win[kh][slot].y, wreg[kh * K + kw].y, r1);
                     }
+                    a0 += r0;
+                    a1 += r1;
                   }
                   a0 = swish(a0);
                   a1 = swish(a1);
@@ -238,7 +250,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
             const int c = tid + i * kDwThreads;
             pv[u][i] = (i < nci && c < C && gb + u < gn) ? s_pool[(gb + u) * C + c] : 0.0f;
           }
-#pragma unroll 4
+#pragma unroll 8
         for (int j = 0; j < P.se; ++j) {
           const float* wrow = P.w_se1 + (size_t)j * C;
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -279,7 +291,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
         float acc[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc[u] = b2;
-#pragma unroll 16
+#pragma unroll 24
         for (int j = 0; j < P.se; ++j) {
           const float wv = __ldg(P.w_se2 + (size_t)j * C + c);
 #pragma unroll
