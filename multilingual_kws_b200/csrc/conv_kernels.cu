@@ -95,7 +95,7 @@ __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
 }
 
 template <int K, int S>
-__global__ void __launch_bounds__(kDwThreads, 2)
+__global__ void __launch_bounds__(kDwThreads)
 dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint16_t* __restrict__ y) {
   extern __shared__ __align__(128) uint8_t smem[];
   const DwSmem L = dw_smem(P, G);
@@ -134,14 +134,6 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
       ptx::mbar_expect_tx(bar, bytes);
       ptx::tma_bulk_g2s(smem, x + (size_t)g0 * clip_words * 2, bytes, bar);
     }
-    // first pass's depthwise weights: issued before the TMA wait so both latencies overlap
-    float2 wreg[K * K];
-    float2 bias = make_float2(0.0f, 0.0f);
-    if (active) {
-#pragma unroll
-      for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp0);
-      bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp0);
-    }
     ptx::mbar_wait(bar, parity);
     parity ^= 1;
     __syncthreads();
@@ -149,11 +141,10 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
     // ---- depthwise conv + BN + swish -> s_out (bf16), channel sums -> s_pool
     if (active) {
       for (int cp = cp0; cp < C2; cp += kDwThreads) {
-        if (cp != cp0) {
+        float2 wreg[K * K];
 #pragma unroll
-          for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp);
-          bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp);
-        }
+        for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp);
+        const float2 bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp);
         for (int g = 0; g < gn; ++g) {
           const uint32_t* in_g = s_in + (size_t)g * clip_words + cp;
           float sum0 = 0.0f, sum1 = 0.0f;
@@ -196,15 +187,12 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
 #pragma unroll
                   for (int kh = 0; kh < K; ++kh) {
                     if (!row_ok[kh]) continue;                    // padded rows contribute nothing (tiny late maps: most rows)
-                    float r0 = 0.0f, r1 = 0.0f;                   // per-row partials: K-deep instead of K*K-deep FMA chains
 #pragma unroll
                     for (int kw = 0; kw < K; ++kw) {
                       const int slot = (j * S + kw) % K;
-                      r0 = fmaf(win[kh][slot].x, wreg[kh * K + kw].x, r0);
-                      r1 = fmaf(win[kh][slot].y, wreg[kh * K + kw].y, r1);
+                      a0 = fmaf(win[kh][slot].x, wreg[kh * K + kw].x, a0);
+                      a1 = fmaf(win[kh][slot].y, wreg[kh * K + kw].y, a1);
                     }
-                    a0 += r0;
-                    a1 += r1;
                   }
                   a0 = swish(a0);
                   a1 = swish(a1);
@@ -235,6 +223,19 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
       __syncthreads();
     }
 
+    if (P.se_external) {
+      // un-gated activation and channel means go to global; the SE GEMMs and the gating pass follow as separate launches
+      const int vecs = gn * npix * (C >> 3);
+      const uint4* src = reinterpret_cast<const uint4*>(s_out);
+      uint4* dst = reinterpret_cast<uint4*>(y) + (size_t)g0 * npix * (C >> 3);
+      for (int i = tid; i < vecs; i += kDwThreads) dst[i] = src[i];
+      uint32_t* pdst = reinterpret_cast<uint32_t*>(P.pooled_out) + (size_t)g0 * C2;
+      for (int i = tid; i < gn * C2; i += kDwThreads)
+        pdst[i] = ptx::pack_h2(s_pool[2 * i] * inv_npix, s_pool[2 * i + 1] * inv_npix, P.bf16);
+      __syncthreads();
+      continue;
+    }
+
     // ---- SE reduce: s[g][j] = swish(b1[j] + mean_g . w1[j][:]).  Every thread owns channels c = tid + 256 i and
     // streams its slice of every weight row (coalesced, independent loads -> deep memory-level parallelism);
     // partial dot products are reduced by warp shuffles, then across the 8 warps through smem.
@@ -250,7 +251,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
             const int c = tid + i * kDwThreads;
             pv[u][i] = (i < nci && c < C && gb + u < gn) ? s_pool[(gb + u) * C + c] : 0.0f;
           }
-#pragma unroll 8
+#pragma unroll 4
         for (int j = 0; j < P.se; ++j) {
           const float* wrow = P.w_se1 + (size_t)j * C;
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -291,7 +292,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
         float acc[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc[u] = b2;
-#pragma unroll 24
+#pragma unroll 16
         for (int j = 0; j < P.se; ++j) {
           const float wv = __ldg(P.w_se2 + (size_t)j * C + c);
 #pragma unroll
@@ -335,7 +336,41 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
   }
 }
 
+// gating pass of the external-SE path: one CTA per clip (grid-stride), 16-byte vectors
+__global__ void __launch_bounds__(256)
+se_scale_kernel(uint16_t* __restrict__ y, const uint16_t* __restrict__ gates, int batch, int npix, int C, int bf16) {
+  const int C8 = C >> 3, tid = threadIdx.x;
+  const int vec_per_clip = npix * C8;
+  const int step = 256 % C8;
+  for (int clip = blockIdx.x; clip < batch; clip += gridDim.x) {
+    uint4* dst = reinterpret_cast<uint4*>(y) + (size_t)clip * vec_per_clip;
+    const uint4* g = reinterpret_cast<const uint4*>(gates) + (size_t)clip * C8;
+    int c8 = tid % C8;
+    for (int i = tid; i < vec_per_clip; i += 256) {
+      const uint4 v = dst[i];
+      const uint4 gv = __ldg(g + c8);
+      float2 a, b;
+      uint4 o;
+      a = ptx::unpack_h2(v.x, bf16); b = ptx::unpack_h2(gv.x, bf16); o.x = ptx::pack_h2(a.x * b.x, a.y * b.y, bf16);
+      a = ptx::unpack_h2(v.y, bf16); b = ptx::unpack_h2(gv.y, bf16); o.y = ptx::pack_h2(a.x * b.x, a.y * b.y, bf16);
+      a = ptx::unpack_h2(v.z, bf16); b = ptx::unpack_h2(gv.z, bf16); o.z = ptx::pack_h2(a.x * b.x, a.y * b.y, bf16);
+      a = ptx::unpack_h2(v.w, bf16); b = ptx::unpack_h2(gv.w, bf16); o.w = ptx::pack_h2(a.x * b.x, a.y * b.y, bf16);
+      dst[i] = o;
+      c8 += step;
+      if (c8 >= C8) c8 -= C8;
+    }
+  }
+}
+
 }  // namespace
+
+int launch_se_scale(void* d_y, const void* d_gates, int batch, int npix, int C, int bf16, int sm_count, cudaStream_t st) {
+  if (batch == 0) return KWS_OK;
+  const int grid = batch < sm_count * 8 ? batch : sm_count * 8;
+  se_scale_kernel<<<grid, 256, 0, st>>>(static_cast<uint16_t*>(d_y), static_cast<const uint16_t*>(d_gates), batch, npix, C, bf16);
+  KWS_CUDA_CHECK(cudaGetLastError());
+  return KWS_OK;
+}
 
 int launch_stem(const float* d_feats, int batch, const StemParams& P, void* d_out, int sm_count,
                 cudaStream_t st) {

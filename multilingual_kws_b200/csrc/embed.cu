@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -85,6 +86,11 @@ struct Op {
   const float* bias = nullptr;
   StemParams stem{};
   DwseParams dw{};
+  // external SE (wide layers): 16-bit GEMM operands, se padded to a multiple of 16
+  int se_pad = 0;
+  const uint16_t* se_w1 = nullptr;   // [se_pad][C]
+  const float* se_b1 = nullptr;       // [se_pad]
+  const uint16_t* se_w2 = nullptr;   // [C][se_pad]
   int dw_group = 1;
   size_t out_elems_per_clip = 0;
   double flops_per_clip = 0;           // 2 * MACs
@@ -110,10 +116,12 @@ struct kws_embed {
   // one) have up to 96 KB of activations per clip and are walked in small chunks so they stay L2-resident; "late"
   // ops have <= 37 KB per clip and run over large chunks so GEMM tiles / depthwise groups fill the 148 SMs.
   int split_op = 0;                    // first late op
+  size_t max_se_channels = 0;          // widest externally-gated layer (scratch: pooled means, squeeze, gates)
   size_t buf_elems[2][3] = {{0, 0, 0}, {0, 0, 0}};   // [segment][X, E, D] per clip, 16-bit elements
   int sm_count = 0, max_smem = 0;
   int chunk = 256;                     // early-segment clips per pass
   int chunk_late = 2048;               // late-segment clips per pass
+  int se_via_gemm = 1;                 // wide layers: SE FCs as batched tcgen05 GEMMs (0: inside the depthwise kernel)
   int bf16 = 0;                        // 16-bit storage / tensor-core operand type: 0 fp16 (default), 1 bf16
   double flops_per_clip = 0;
 };
@@ -171,6 +179,13 @@ struct Builder {
     return upload(m, h, &cerr);
   }
   const float* vec(const std::vector<float>& v) { return upload(m, v, &cerr); }
+  uint16_t h16(float v) const {
+    uint16_t bits;
+    if (m->bf16) { const __nv_bfloat16 b = __float2bfloat16(v); memcpy(&bits, &b, 2); }
+    else { const __half b = __float2half_rn(v); memcpy(&bits, &b, 2); }
+    return bits;
+  }
+  const uint16_t* vec16(const std::vector<uint16_t>& v) { return upload(m, v, &cerr); }
 };
 
 }  // namespace
@@ -189,6 +204,7 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
   kws_embed* m = new (std::nothrow) kws_embed();
   KWS_REQUIRE(m != nullptr, "out of host memory");
   m->bf16 = act_dtype;
+  if (const char* env = getenv("KWS_SE_IN_KERNEL")) m->se_via_gemm = atoi(env) ? 0 : 1;   // tuning knob (A/B measurements)
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -294,6 +310,26 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
         P.w_se2 = B.vec(std::vector<float>(w2->data, w2->data + (size_t)se * cexp));
         P.b_se2 = B.vec(std::vector<float>(b2->data, b2->data + cexp));
         CK(P.w_dw && P.b_dw && P.w_se1 && P.b_se1 && P.w_se2 && P.b_se2);
+        P.se_external = 0; P.pooled_out = nullptr;
+        if (cexp >= 240 && m->se_via_gemm) {
+          // wide layer: SE as two batched tensor-core GEMMs.  FC1: [B,C] x W1[se_pad,C]^T (+b1, swish);
+          // FC2: [B,se_pad] x W2[C,se_pad]^T (+b2, sigmoid).  Padding rows / columns are zero.
+          const int sp = (se + 15) & ~15;
+          std::vector<uint16_t> w1h((size_t)sp * cexp, B.h16(0.0f)), w2h((size_t)cexp * sp, B.h16(0.0f));
+          std::vector<float> b1p(sp, 0.0f);
+          for (int j = 0; j < se; ++j) {
+            b1p[j] = b1->data[j];
+            for (int ch = 0; ch < cexp; ++ch) {
+              w1h[(size_t)j * cexp + ch] = B.h16(w1->data[(size_t)ch * se + j]);
+              w2h[(size_t)ch * sp + j] = B.h16(w2->data[(size_t)j * cexp + ch]);
+            }
+          }
+          P.se_external = 1;
+          op.se_pad = sp;
+          op.se_w1 = B.vec16(w1h); op.se_b1 = B.vec(b1p); op.se_w2 = B.vec16(w2h);
+          CK(op.se_w1 && op.se_b1 && op.se_w2);
+          if ((size_t)cexp > m->max_se_channels) m->max_se_channels = (size_t)cexp;
+        }
         op.dw_group = dwse_pick_group(P, m->max_smem, 1 << 20, m->sm_count);
         if (op.dw_group < 1) { B.err = "depthwise layer " + n + " does not fit shared memory"; return fail(KWS_ERR_UNSUPPORTED); }
         macs += (double)P.Ho * P.Wo * cexp * k * k + 2.0 * cexp * se;
@@ -467,7 +503,12 @@ extern "C" int kws_embed_launches(const kws_embed_t* m, int batch) {
   if (!m || batch <= 0) return 0;
   const int ce = batch < m->chunk ? batch : m->chunk, cl = batch < m->chunk_late ? batch : m->chunk_late;
   const int n_ops = (int)m->ops.size();
-  return ((batch + ce - 1) / ce) * m->split_op + ((batch + cl - 1) / cl) * (n_ops - m->split_op);
+  int launches = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    const int per = (m->ops[i].kind == kOpDwse && m->ops[i].dw.se_external) ? 4 : 1;   // dw+pool, 2 SE GEMMs, gating
+    launches += per * (i < m->split_op ? (batch + ce - 1) / ce : (batch + cl - 1) / cl);
+  }
+  return launches;
 }
 
 extern "C" int kws_embed_set_graph(kws_embed_t* m, int enable) {
@@ -482,7 +523,8 @@ extern "C" size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch) {
   const size_t cl = (size_t)(batch < m->chunk_late ? batch : m->chunk_late);
   const size_t early = (m->buf_elems[0][0] + m->buf_elems[0][1] + m->buf_elems[0][2]) * ce;
   const size_t late = m->buf_elems[1][0] * (size_t)batch + (m->buf_elems[1][1] + m->buf_elems[1][2]) * cl;
-  return (early + late) * 2 + 2048;
+  const size_t se_scratch = (ce > cl ? ce : cl) * (2 * m->max_se_channels + 64);   // pooled means, gates, squeeze (16-bit)
+  return (early + late + se_scratch) * 2 + 4096;
 }
 
 // tap_op >= 0: additionally copy the output of op `tap_op` (bf16 NHWC, or fp32 for the last op) to d_tap.
@@ -547,6 +589,11 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
   uint16_t* H = early[2] + m->buf_elems[0][2] * chunk_seg[0];
   uint16_t* late_e = H + m->buf_elems[1][0] * (size_t)batch;
   uint16_t* late_d = late_e + m->buf_elems[1][1] * chunk_seg[1];
+  const size_t se_rows = (size_t)(chunk_seg[0] > chunk_seg[1] ? chunk_seg[0] : chunk_seg[1]);
+  uint16_t* se_pooled = reinterpret_cast<uint16_t*>(
+      (reinterpret_cast<uintptr_t>(late_d + m->buf_elems[1][2] * chunk_seg[1]) + 255) & ~(uintptr_t)255);
+  uint16_t* se_gates = se_pooled + se_rows * m->max_se_channels;
+  uint16_t* se_squeeze = se_gates + se_rows * m->max_se_channels;
 
   std::vector<cudaEvent_t> evs;
   size_t ev_i = 0;
@@ -581,8 +628,21 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
         if (op.kind == kOpStem) {
           rc = launch_stem(d_feats + (size_t)b0 * m->H * m->W, nb, op.stem, out_ptr, m->sm_count, st);
         } else if (op.kind == kOpDwse) {
-          rc = launch_dwse(bufs[op.in_buf], nb, op.dw, out_ptr, dwse_pick_group(op.dw, m->max_smem, nb, m->sm_count),
-                           m->sm_count, st);
+          DwseParams P = op.dw;
+          P.pooled_out = se_pooled;
+          rc = launch_dwse(bufs[op.in_buf], nb, P, out_ptr, dwse_pick_group(P, m->max_smem, nb, m->sm_count), m->sm_count, st);
+          if (rc == KWS_OK && P.se_external) {
+            GemmEpilogue e1;
+            e1.bias = op.se_b1; e1.residual = nullptr; e1.out = se_squeeze; e1.ldo = op.se_pad; e1.ldr = op.se_pad;
+            e1.act = kActSwish; e1.out_f32 = 0; e1.gap4 = 0; e1.bf16 = m->bf16;
+            rc = gemm_h16(se_pooled, op.se_w1, nb, op.se_pad, P.C, 0, e1, m->sm_count, st);
+            if (rc == KWS_OK) {
+              GemmEpilogue e2 = e1;
+              e2.bias = P.b_se2; e2.out = se_gates; e2.ldo = P.C; e2.ldr = P.C; e2.act = kActSigmoid;
+              rc = gemm_h16(se_squeeze, op.se_w2, nb, P.C, op.se_pad, 0, e2, m->sm_count, st);
+            }
+            if (rc == KWS_OK) rc = launch_se_scale(out_ptr, se_gates, nb, P.Ho * P.Wo, P.C, m->bf16, m->sm_count, st);
+          }
         } else {
           GemmEpilogue ep;
           ep.bias = op.bias;
