@@ -150,6 +150,8 @@ def run_ours(args, rank, local_rank, world):
     weights = W.random_init(0, randomize_bn=True, residual_gamma_scale=0.3)
     emb_model = EmbeddingModel(weights, chunk=args.chunk, dtype=args.dtype)
     emb_model.set_chunk_late(args.chunk_late)
+    if args.no_graph:
+        emb_model.set_graph(False)      # plain launches (needed under ncu: kernels inside a graph capture cannot be profiled)
     base = synthetic_pcm(min(B, 256), cfg_id=2 + rank)
     pcm_host = np.tile(base, (-(-B // base.shape[0]), 1))[:B]
     pcm = torch.from_numpy(pcm_host).to(dev)
@@ -337,6 +339,7 @@ def main():
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--ref-sample", type=int, default=1024, help="clips per reference / cpu_baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying the CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -94,7 +94,46 @@ __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
   return L;
 }
 
-template <int K, int S>
+// Tiny late-stage maps (<= 7x5 in, <= 4x3 out): the whole (clip, channel-pair) image lives in registers and every
+// bound is a compile-time constant, so only the taps that actually overlap the image are executed, with no branches.
+template <int K, int S, int H, int W, int PT, int PLFT>
+struct SmallGeom {
+  static constexpr int HO = S == 1 ? H : (H + PT + K / 2 - K) / 2 + 1;
+  static constexpr int WO = S == 1 ? W : (W + PLFT + K / 2 - K) / 2 + 1;
+};
+template <int K, int S, int H, int W, int PT, int PLFT>
+__device__ __forceinline__ void dw_small_item(const uint32_t* __restrict__ in_g, int C2, const float2 (&wreg)[K * K],
+                                              float2 bias, int bf16, uint32_t* __restrict__ out_g, float& sum0,
+                                              float& sum1) {
+  using G = SmallGeom<K, S, H, W, PT, PLFT>;
+  float2 x[H * W];
+#pragma unroll
+  for (int q = 0; q < H * W; ++q) x[q] = ptx::unpack_h2(in_g[(size_t)q * C2], bf16);
+#pragma unroll
+  for (int ho = 0; ho < G::HO; ++ho)
+#pragma unroll
+    for (int wo = 0; wo < G::WO; ++wo) {
+      float a0 = bias.x, a1 = bias.y;
+#pragma unroll
+      for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
+          const int r = ho * S + kh - PT, c = wo * S + kw - PLFT;     // compile-time after unrolling
+          if (r >= 0 && r < H && c >= 0 && c < W) {
+            a0 = fmaf(x[r * W + c].x, wreg[kh * K + kw].x, a0);
+            a1 = fmaf(x[r * W + c].y, wreg[kh * K + kw].y, a1);
+          }
+        }
+      a0 = swish(a0);
+      a1 = swish(a1);
+      sum0 += a0;
+      sum1 += a1;
+      out_g[(size_t)(ho * G::WO + wo) * C2] = ptx::pack_h2(a0, a1, bf16);
+    }
+}
+
+// GEOM: 0 = generic (runtime geometry, row strips); 1..6 = the tiny-map geometries of EfficientNet-B0 at 49x40 input.
+template <int K, int S, int GEOM>
 __global__ void __launch_bounds__(kDwThreads)
 dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint16_t* __restrict__ y) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -138,8 +177,26 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
     parity ^= 1;
     __syncthreads();
 
-    // ---- depthwise conv + BN + swish -> s_out (bf16), channel sums -> s_pool
-    if (active) {
+    // ---- depthwise conv + BN + swish -> s_out (16-bit), channel sums -> s_pool
+    if constexpr (GEOM != 0) {
+      // balanced flat loop over (clip, channel pair) items: one thread computes every output pixel of its item
+      constexpr int H = GEOM == 1 ? 7 : (GEOM <= 4 ? 4 : 2);
+      constexpr int W = GEOM == 1 ? 5 : (GEOM <= 4 ? 3 : 2);
+      constexpr int PT = (GEOM == 3 || GEOM == 5) ? 2 : 1;
+      constexpr int PLFT = (GEOM == 3 || GEOM == 4 || GEOM == 5) ? 2 : 1;
+      for (int item = tid; item < C2 * gn; item += kDwThreads) {
+        const int g = item / C2, cp = item - g * C2;
+        float2 wreg[K * K];
+#pragma unroll
+        for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp);
+        const float2 bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp);
+        float sum0 = 0.0f, sum1 = 0.0f;
+        dw_small_item<K, S, H, W, PT, PLFT>(s_in + (size_t)g * clip_words + cp, C2, wreg, bias, P.bf16,
+                                            s_out + (size_t)g * npix * C2 + cp, sum0, sum1);
+        s_pool[g * C + 2 * cp] = sum0;
+        s_pool[g * C + 2 * cp + 1] = sum1;
+      }
+    } else if (active) {
       for (int cp = cp0; cp < C2; cp += kDwThreads) {
         float2 wreg[K * K];
 #pragma unroll
@@ -214,7 +271,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
       }
     }
     __syncthreads();
-    if (PL > 1) {                     // fixed-order sum over pixel lanes: results do not depend on scheduling
+    if (GEOM == 0 && PL > 1) {        // fixed-order sum over pixel lanes: results do not depend on scheduling
       for (int i = tid; i < gn * C; i += kDwThreads) {
         float a = 0.0f;
         for (int q = 0; q < PL; ++q) a += s_part[q * gn * C + i];
@@ -402,7 +459,17 @@ int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int 
   KWS_REQUIRE((P.K == 3 || P.K == 5) && (P.S == 1 || P.S == 2), "dwse: unsupported kernel %d / stride %d", P.K, P.S);
   const size_t smem = dw_smem(P, G).total;
   void (*kern)(const uint16_t*, int, int, DwseParams, uint16_t*) =
-      P.K == 3 ? (P.S == 1 ? dwse_kernel<3, 1> : dwse_kernel<3, 2>) : (P.S == 1 ? dwse_kernel<5, 1> : dwse_kernel<5, 2>);
+      P.K == 3 ? (P.S == 1 ? dwse_kernel<3, 1, 0> : dwse_kernel<3, 2, 0>) : (P.S == 1 ? dwse_kernel<5, 1, 0> : dwse_kernel<5, 2, 0>);
+  // tiny-map specialisations (geometry must match exactly, else the generic kernel handles it)
+  auto is = [&](int k, int s_, int h, int w, int pt, int pl) {
+    return P.K == k && P.S == s_ && P.H == h && P.W == w && P.pad_top == pt && P.pad_left == pl;
+  };
+  if (is(3, 2, 7, 5, 1, 1)) kern = dwse_kernel<3, 2, 1>;
+  else if (is(3, 1, 4, 3, 1, 1)) kern = dwse_kernel<3, 1, 2>;
+  else if (is(5, 1, 4, 3, 2, 2)) kern = dwse_kernel<5, 1, 3>;
+  else if (is(5, 2, 4, 3, 1, 2)) kern = dwse_kernel<5, 2, 4>;
+  else if (is(5, 1, 2, 2, 2, 2)) kern = dwse_kernel<5, 1, 5>;
+  else if (is(3, 1, 2, 2, 1, 1)) kern = dwse_kernel<3, 1, 6>;
   KWS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_groups = (batch + G - 1) / G;
   const int per_sm = smem <= 100 * 1024 ? 2 : 1;
