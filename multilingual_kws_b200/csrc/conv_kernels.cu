@@ -36,18 +36,28 @@ stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, uint1
   for (int i = tid; i < 9 * kStemC; i += kStemThreads) s_w[i] = P.w[i];
   if (tid < kStemC) s_b[tid] = P.bias[tid];
   const int npix = P.Ho * P.Wo;
+  __syncthreads();
+  // item = (pixel, group of 8 output channels); 256 % 4 == 0, so a thread's channel group never changes and its
+  // 72 weights + 8 biases live in registers for the whole kernel
+  const int g = tid & 3;
+  float wr[9][8], br[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] = s_w[t * kStemC + g * 8 + j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) br[j] = s_b[g * 8 + j];
   for (int clip = blockIdx.x; clip < batch; clip += gridDim.x) {
     __syncthreads();
     const float* src = feats + (size_t)clip * P.H * P.W;
     for (int i = tid; i < P.H * P.W; i += kStemThreads) s_in[i] = fmaf(__ldg(src + i), P.in_scale, P.in_shift);
     __syncthreads();
-    // item = (pixel, group of 8 output channels)
     for (int item = tid; item < npix * 4; item += kStemThreads) {
-      const int p = item >> 2, g = item & 3;
+      const int p = item >> 2;
       const int ho = p / P.Wo, wo = p - ho * P.Wo;
       float acc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = s_b[g * 8 + j];
+      for (int j = 0; j < 8; ++j) acc[j] = br[j];
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int r = ho * 2 + kh - P.pad_top;
@@ -57,9 +67,8 @@ stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, uint1
           const int c = wo * 2 + kw - P.pad_left;
           if (c < 0 || c >= P.W) continue;
           const float x = s_in[r * P.W + c];
-          const float* wv = s_w + (kh * 3 + kw) * kStemC + g * 8;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, wv[j], acc[j]);
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, wr[kh * 3 + kw][j], acc[j]);
         }
       }
       uint4 pk;
@@ -76,7 +85,7 @@ stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, uint1
 constexpr int kDwThreads = 256;
 
 struct DwSmem {
-  uint32_t in_bytes, out_off, pooled_off, part_off, s_off, red_off, bar_off, total;
+  uint32_t in_bytes, out_off, pooled_off, part_off, s_off, red_off, bar_off, w_off, w_floats, total;
   int PL;   // pixel lanes per channel pair
 };
 __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
@@ -90,7 +99,12 @@ __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
   L.s_off = L.part_off + (L.PL > 1 ? (uint32_t)L.PL * G * P.C * 4 : 0u);
   L.red_off = (L.s_off + (uint32_t)G * P.se * 4 + 15) & ~15u;                            // [se][8 warps][4 clips] FC1 partials
   L.bar_off = (L.red_off + (uint32_t)P.se * (kDwThreads / 32) * 4 * 4 + 15) & ~15u;
-  L.total = L.bar_off + 16;
+  // Narrow layers keep ALL their weights (depthwise, both SE matrices, biases) resident in smem for the lifetime of
+  // the persistent CTA, so no phase waits on a global-memory round trip; wide layers read them through L1/L2.
+  L.w_floats = (uint32_t)(P.K * P.K * P.C + P.C + (P.se_external ? 0 : 2 * P.se * P.C + P.se + P.C));
+  L.w_off = (L.bar_off + 16 + 15) & ~15u;
+  if (L.w_floats * 4 > 40 * 1024) L.w_floats = 0;
+  L.total = L.w_off + L.w_floats * 4;
   return L;
 }
 
@@ -151,6 +165,23 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
   const int clip_words = P.H * P.W * C2;
   const float inv_npix = 1.0f / (float)npix;
 
+  // weight pointers: smem-resident copies for narrow layers, global (L1/L2) otherwise
+  const float *w_dw = P.w_dw, *b_dw = P.b_dw, *w_se1 = P.w_se1, *b_se1 = P.b_se1, *w_se2 = P.w_se2, *b_se2 = P.b_se2;
+  if (L.w_floats) {
+    float* sw = reinterpret_cast<float*>(smem + L.w_off);
+    const int n_dw = K * K * P.C;
+    for (int i = tid; i < n_dw; i += kDwThreads) sw[i] = __ldg(P.w_dw + i);
+    for (int i = tid; i < P.C; i += kDwThreads) sw[n_dw + i] = __ldg(P.b_dw + i);
+    w_dw = sw; b_dw = sw + n_dw;
+    if (!P.se_external) {
+      float* q = sw + n_dw + P.C;
+      const int n_se = P.se * P.C;
+      for (int i = tid; i < n_se; i += kDwThreads) { q[i] = __ldg(P.w_se1 + i); q[n_se + P.se + i] = __ldg(P.w_se2 + i); }
+      for (int i = tid; i < P.se; i += kDwThreads) q[n_se + i] = __ldg(P.b_se1 + i);
+      for (int i = tid; i < P.C; i += kDwThreads) q[2 * n_se + P.se + i] = __ldg(P.b_se2 + i);
+      w_se1 = q; b_se1 = q + n_se; w_se2 = q + n_se + P.se; b_se2 = q + 2 * n_se + P.se;
+    }
+  }
   if (tid == 0) {
     ptx::mbar_init(bar, 1);
     ptx::fence_barrier_init();
@@ -188,8 +219,8 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
         const int g = item / C2, cp = item - g * C2;
         float2 wreg[K * K];
 #pragma unroll
-        for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp);
-        const float2 bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp);
+        for (int kk = 0; kk < K * K; ++kk) wreg[kk] = *(reinterpret_cast<const float2*>(w_dw + (size_t)kk * C) + cp);
+        const float2 bias = *(reinterpret_cast<const float2*>(b_dw) + cp);
         float sum0 = 0.0f, sum1 = 0.0f;
         dw_small_item<K, S, H, W, PT, PLFT>(s_in + (size_t)g * clip_words + cp, C2, wreg, bias, P.bf16,
                                             s_out + (size_t)g * npix * C2 + cp, sum0, sum1);
@@ -200,8 +231,8 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
       for (int cp = cp0; cp < C2; cp += kDwThreads) {
         float2 wreg[K * K];
 #pragma unroll
-        for (int kk = 0; kk < K * K; ++kk) wreg[kk] = __ldg(reinterpret_cast<const float2*>(P.w_dw + (size_t)kk * C) + cp);
-        const float2 bias = __ldg(reinterpret_cast<const float2*>(P.b_dw) + cp);
+        for (int kk = 0; kk < K * K; ++kk) wreg[kk] = *(reinterpret_cast<const float2*>(w_dw + (size_t)kk * C) + cp);
+        const float2 bias = *(reinterpret_cast<const float2*>(b_dw) + cp);
         for (int g = 0; g < gn; ++g) {
           const uint32_t* in_g = s_in + (size_t)g * clip_words + cp;
           float sum0 = 0.0f, sum1 = 0.0f;
@@ -310,13 +341,13 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
           }
 #pragma unroll 4
         for (int j = 0; j < P.se; ++j) {
-          const float* wrow = P.w_se1 + (size_t)j * C;
+          const float* wrow = w_se1 + (size_t)j * C;
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
           for (int i = 0; i < kMaxCi; ++i) {
             const int c = tid + i * kDwThreads;
             if (i < nci && c < C) {
-              const float wv = __ldg(wrow + c);
+              const float wv = wrow[c];
               a0 = fmaf(wv, pv[0][i], a0); a1 = fmaf(wv, pv[1][i], a1);
               a2 = fmaf(wv, pv[2][i], a2); a3 = fmaf(wv, pv[3][i], a3);
             }
@@ -335,7 +366,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
             float a = 0.f;
 #pragma unroll
             for (int wv = 0; wv < kDwThreads / 32; ++wv) a += s_red[(j * (kDwThreads / 32) + wv) * 4 + u];
-            s_se[(gb + u) * P.se + j] = swish(a * inv_npix + __ldg(P.b_se1 + j));
+            s_se[(gb + u) * P.se + j] = swish(a * inv_npix + b_se1[j]);
           }
         }
         __syncthreads();
@@ -344,14 +375,14 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
 
     // ---- SE expand: gate[g][c] = sigmoid(b2[c] + s[g] . w2[:][c])  (overwrites the pooled sums)
     for (int c = tid; c < C; c += kDwThreads) {
-      const float b2 = __ldg(P.b_se2 + c);
+      const float b2 = b_se2[c];
       for (int gb = 0; gb < gn; gb += 8) {
         float acc[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc[u] = b2;
 #pragma unroll 16
         for (int j = 0; j < P.se; ++j) {
-          const float wv = __ldg(P.w_se2 + (size_t)j * C + c);
+          const float wv = w_se2[(size_t)j * C + c];
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             if (gb + u < gn) acc[u] = fmaf(wv, s_se[(gb + u) * P.se + j], acc[u]);

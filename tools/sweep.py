@@ -34,5 +34,4 @@ for B in (1024, 4096):
         print(json.dumps(dict(B=B, chunk=chunk, late=late, ms=round(float(np.median(ts)), 3), utt_s=round(B / np.median(ts) * 1e3),
                               launches=m.launches(B), per_kind={k: round(v, 3) for k, v in agg.items()})))
         if B == 1024 and chunk == 256 and late == 2048:
-            top = sorted(zip(ms, [i[0] for i in m.op_info()]), reverse=True)[:12]
-            print("  top ops:", [(n, round(float(t), 3)) for t, n in top])
+            print("  all ops (us):", [(n.replace("block", "b").replace("_activation", "").replace("_se_excite", "_dw"), int(round(float(t) * 1000))) for t, n in zip(ms, [i[0] for i in m.op_info()])])
