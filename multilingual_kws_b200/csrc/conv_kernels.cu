@@ -146,7 +146,52 @@ __device__ __forceinline__ void dw_small_item(const uint32_t* __restrict__ in_g,
     }
 }
 
-// GEOM: 0 = generic (runtime geometry, row strips); 1..6 = the tiny-map geometries of EfficientNet-B0 at 49x40 input.
+// Early-stage maps (25x20 ... 7x5): one output ROW per call with every column bound, smem offset and window slot a
+// compile-time constant (geometry, stride, padding and channel count are template parameters), so the row costs
+// K*S shared loads + K*K*2 FMAs per output pixel and no branches; padded rows are handled by zero-selects.
+template <int K, int S, int W, int WO, int PLFT, int C2>
+__device__ __forceinline__ void dw_strip_row(const uint32_t* const (&rowp)[K], const bool (&row_ok)[K],
+                                             const float2 (&wreg)[K * K], float2 bias, int bf16,
+                                             uint32_t* __restrict__ orow, float& sum0, float& sum1) {
+  float2 win[K][K];
+#pragma unroll
+  for (int wo = 0; wo < WO; ++wo) {
+#pragma unroll
+    for (int kw = 0; kw < K; ++kw) {
+      if (kw >= K - S || wo == 0) {                      // compile-time: the columns that enter the window here
+        const int c = wo * S + kw - PLFT;
+        const int slot = (wo * S + kw) % K;
+#pragma unroll
+        for (int kh = 0; kh < K; ++kh) {
+          float2 v = make_float2(0.0f, 0.0f);
+          if (c >= 0 && c < W) {                         // compile-time
+            const float2 t = ptx::unpack_h2(rowp[kh][c * C2], bf16);
+            v.x = row_ok[kh] ? t.x : 0.0f;
+            v.y = row_ok[kh] ? t.y : 0.0f;
+          }
+          win[kh][slot] = v;
+        }
+      }
+    }
+    float a0 = bias.x, a1 = bias.y;
+#pragma unroll
+    for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < K; ++kw) {
+        const int slot = (wo * S + kw) % K;
+        a0 = fmaf(win[kh][slot].x, wreg[kh * K + kw].x, a0);
+        a1 = fmaf(win[kh][slot].y, wreg[kh * K + kw].y, a1);
+      }
+    a0 = swish(a0);
+    a1 = swish(a1);
+    sum0 += a0;
+    sum1 += a1;
+    orow[wo * C2] = ptx::pack_h2(a0, a1, bf16);
+  }
+}
+
+// GEOM: 0 = generic (runtime geometry, row strips); 1..6 = the tiny-map geometries of EfficientNet-B0 at 49x40 input
+// (whole image in registers); 7..11 = its early-stage geometries (compile-time row strips).
 template <int K, int S, int GEOM>
 __global__ void __launch_bounds__(kDwThreads)
 dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint16_t* __restrict__ y) {
@@ -209,7 +254,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
     __syncthreads();
 
     // ---- depthwise conv + BN + swish -> s_out (16-bit), channel sums -> s_pool
-    if constexpr (GEOM != 0) {
+    if constexpr (GEOM >= 1 && GEOM <= 6) {
       // balanced flat loop over (clip, channel pair) items: one thread computes every output pixel of its item
       constexpr int H = GEOM == 1 ? 7 : (GEOM <= 4 ? 4 : 2);
       constexpr int W = GEOM == 1 ? 5 : (GEOM <= 4 ? 3 : 2);
@@ -248,8 +293,18 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
               row_ok[kh] = (r >= 0) && (r < P.H);
               rowp[kh] = in_g + (size_t)(row_ok[kh] ? r : 0) * P.W * C2;
             }
-            float2 win[K][K];
             uint32_t* orow = s_out + ((size_t)g * npix + (size_t)ho * P.Wo) * C2 + cp;
+            if constexpr (GEOM >= 7) {
+              // block1a 25x20 k3 s1 C32 | block2a 25x20 k3 s2 C96 | block2b 13x10 k3 s1 C144 | block3a 13x10 k5 s2 C144 |
+              // block3b 7x5 k5 s1 C240
+              constexpr int GW = GEOM <= 8 ? 20 : (GEOM <= 10 ? 10 : 5);
+              constexpr int GWO = GEOM == 7 ? 20 : (GEOM <= 9 ? 10 : 5);
+              constexpr int GPL = (GEOM == 8) ? 0 : ((GEOM == 11) ? 2 : 1);
+              constexpr int GC2 = GEOM == 7 ? 16 : (GEOM == 8 ? 48 : (GEOM <= 10 ? 72 : 120));
+              dw_strip_row<K, S, GW, GWO, GPL, GC2>(rowp, row_ok, wreg, bias, P.bf16, orow, sum0, sum1);
+              continue;
+            }
+            float2 win[K][K];
             for (int wo_base = 0; wo_base < P.Wo; wo_base += K) {
 #pragma unroll
               for (int j = 0; j < K; ++j) {
@@ -302,7 +357,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
       }
     }
     __syncthreads();
-    if (GEOM == 0 && PL > 1) {        // fixed-order sum over pixel lanes: results do not depend on scheduling
+    if ((GEOM == 0 || GEOM >= 7) && PL > 1) {   // fixed-order sum over pixel lanes: results do not depend on scheduling
       for (int i = tid; i < gn * C; i += kDwThreads) {
         float a = 0.0f;
         for (int q = 0; q < PL; ++q) a += s_part[q * gn * C + i];
@@ -501,6 +556,11 @@ int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int 
   else if (is(5, 2, 4, 3, 1, 2)) kern = dwse_kernel<5, 2, 4>;
   else if (is(5, 1, 2, 2, 2, 2)) kern = dwse_kernel<5, 1, 5>;
   else if (is(3, 1, 2, 2, 1, 1)) kern = dwse_kernel<3, 1, 6>;
+  else if (is(3, 1, 25, 20, 1, 1) && P.C == 32) kern = dwse_kernel<3, 1, 7>;
+  else if (is(3, 2, 25, 20, 1, 0) && P.C == 96) kern = dwse_kernel<3, 2, 8>;
+  else if (is(3, 1, 13, 10, 1, 1) && P.C == 144) kern = dwse_kernel<3, 1, 9>;
+  else if (is(5, 2, 13, 10, 2, 1) && P.C == 144) kern = dwse_kernel<5, 2, 10>;
+  else if (is(5, 1, 7, 5, 2, 2) && P.C == 240) kern = dwse_kernel<5, 1, 11>;
   KWS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_groups = (batch + G - 1) / G;
   const int per_sm = smem <= 100 * 1024 ? 2 : 1;
