@@ -200,10 +200,11 @@ def run_ours(args, rank, local_rank, world):
     pcm_pinned = torch.from_numpy(pcm_host).pin_memory()
     emb_pinned = torch.empty((B, emb_model.output_dim), dtype=torch.float32).pin_memory()
 
+    from multilingual_kws_b200.pipeline import EmbedPipeline
+    pipe = EmbedPipeline(fe, emb_model, n_samples=16000, sub_batch=max(1, B // 2))
+
     def step_e2e():
-        d = pcm_pinned.to(dev, non_blocking=True)
-        f = fe.forward(d, out_scale=FEATURE_SCALE)
-        emb_pinned.copy_(emb_model.forward_device(f), non_blocking=True)
+        pipe.run_host(pcm_pinned, emb_pinned)       # copies overlap the kernels of the neighbouring sub-batch
 
     ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
     e2e_value = world * B / (ms_e2e * 1e-3)
@@ -334,8 +335,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="clips per GPU per step")
-    ap.add_argument("--chunk", type=int, default=256, help="clips per pass through the layer list")
-    ap.add_argument("--chunk-late", type=int, default=2048, help="clips per pass for the late (small-activation) layers")
+    ap.add_argument("--chunk", type=int, default=1024, help="clips per pass for the early (large-activation) layers")
+    ap.add_argument("--chunk-late", type=int, default=4096, help="clips per pass for the late (small-activation) layers")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--ref-sample", type=int, default=1024, help="clips per reference / cpu_baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

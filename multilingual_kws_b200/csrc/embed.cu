@@ -119,8 +119,8 @@ struct kws_embed {
   size_t max_se_channels = 0;          // widest externally-gated layer (scratch: pooled means, squeeze, gates)
   size_t buf_elems[2][3] = {{0, 0, 0}, {0, 0, 0}};   // [segment][X, E, D] per clip, 16-bit elements
   int sm_count = 0, max_smem = 0;
-  int chunk = 256;                     // early-segment clips per pass
-  int chunk_late = 2048;               // late-segment clips per pass
+  int chunk = 1024;                    // early-segment clips per pass
+  int chunk_late = 4096;               // late-segment clips per pass
   int se_via_gemm = 1;                 // wide layers: SE FCs as batched tcgen05 GEMMs (0: inside the depthwise kernel)
   int bf16 = 0;                        // 16-bit storage / tensor-core operand type: 0 fp16 (default), 1 bf16
   double flops_per_clip = 0;
@@ -505,7 +505,7 @@ extern "C" int kws_embed_launches(const kws_embed_t* m, int batch) {
   const int n_ops = (int)m->ops.size();
   int launches = 0;
   for (int i = 0; i < n_ops; ++i) {
-    const int per = (m->ops[i].kind == kOpDwse && m->ops[i].dw.se_external) ? 4 : 1;   // dw+pool, 2 SE GEMMs, gating
+    const int per = (m->ops[i].kind == kOpDwse && m->ops[i].dw.se_external) ? 3 : 1;   // dw+pool, 2 SE GEMMs (2nd one gates)
     launches += per * (i < m->split_op ? (batch + ce - 1) / ce : (batch + cl - 1) / cl);
   }
   return launches;
@@ -634,14 +634,15 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
           if (rc == KWS_OK && P.se_external) {
             GemmEpilogue e1;
             e1.bias = op.se_b1; e1.residual = nullptr; e1.out = se_squeeze; e1.ldo = op.se_pad; e1.ldr = op.se_pad;
-            e1.act = kActSwish; e1.out_f32 = 0; e1.gap4 = 0; e1.bf16 = m->bf16;
+            e1.act = kActSwish; e1.out_f32 = 0; e1.gap4 = 0; e1.bf16 = m->bf16; e1.scale_target = nullptr; e1.scale_npix = 0;
             rc = gemm_h16(se_pooled, op.se_w1, nb, op.se_pad, P.C, 0, e1, m->sm_count, st);
             if (rc == KWS_OK) {
               GemmEpilogue e2 = e1;
+              // expand FC + sigmoid; its epilogue applies the gates to the activation in place (no gates tensor, no extra pass)
               e2.bias = P.b_se2; e2.out = se_gates; e2.ldo = P.C; e2.ldr = P.C; e2.act = kActSigmoid;
+              e2.scale_target = out_ptr; e2.scale_npix = P.Ho * P.Wo;
               rc = gemm_h16(se_squeeze, op.se_w2, nb, P.C, op.se_pad, 0, e2, m->sm_count, st);
             }
-            if (rc == KWS_OK) rc = launch_se_scale(out_ptr, se_gates, nb, P.Ho * P.Wo, P.C, m->bf16, m->sm_count, st);
           }
         } else {
           GemmEpilogue ep;
@@ -649,6 +650,7 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
           ep.residual = op.res_buf >= 0 ? bufs[op.res_buf] : nullptr;
           ep.out = out_ptr; ep.ldo = op.N; ep.ldr = op.N;
           ep.act = op.act; ep.out_f32 = op.out_f32; ep.gap4 = op.gap4; ep.bf16 = m->bf16;
+          ep.scale_target = nullptr; ep.scale_npix = 0;
           rc = gemm_h16(bufs[op.in_buf], op.w, op.rows_per_clip * nb, op.N, op.K, 0, ep, m->sm_count, st);
         }
         if (rc != KWS_OK) return rc;
@@ -704,5 +706,6 @@ extern "C" int kws_gemm_h16(const void* d_a, const void* d_w, int M, int N, int 
   GemmEpilogue ep;
   ep.bias = d_bias; ep.residual = d_residual;
   ep.out = d_out; ep.ldo = N; ep.ldr = N; ep.act = act; ep.out_f32 = out_f32; ep.gap4 = gap4; ep.bf16 = dtype;
+  ep.scale_target = nullptr; ep.scale_npix = 0;
   return gemm_h16(d_a, d_w, M, N, K, block_n, ep, sm, (cudaStream_t)stream);
 }

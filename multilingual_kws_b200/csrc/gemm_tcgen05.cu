@@ -50,13 +50,18 @@ struct EpiCtx {
 };
 
 // One 16-column chunk of one accumulator row: bias, activation, residual, optional 4-row mean, store.
+// ACT / RES / GAP are compile-time for the configurations the embedding tower uses (-1 = read from `ep` at run time).
+template <int ACT, int RES, int GAP>
 __device__ __forceinline__ void epilogue_chunk(const EpiCtx& c, const uint32_t (&r)[16], int c0) {
   const GemmShape& sh = c.sh;
   const GemmEpilogue& ep = c.ep;
+  const int act = ACT >= 0 ? ACT : ep.act;
+  const bool has_res = RES >= 0 ? (RES != 0) : (ep.residual != nullptr);
+  const bool gap4 = GAP >= 0 ? (GAP != 0) : (ep.gap4 != 0);
   const int n_base = c.n_t * sh.block_n + c0;
   uint4 rr[2];
   rr[0] = rr[1] = make_uint4(0u, 0u, 0u, 0u);
-  if (ep.residual && c.row_ok) {     // plain (coherent) loads: the residual may alias the output (in-place skip)
+  if (has_res && c.row_ok) {         // plain (coherent) loads: the residual may alias the output (in-place skip)
     const uint16_t* rp = static_cast<const uint16_t*>(ep.residual) + (size_t)c.row * ep.ldr + n_base;
     rr[0] = *reinterpret_cast<const uint4*>(rp);
     if (n_base + 8 < sh.N) rr[1] = *reinterpret_cast<const uint4*>(rp + 8);
@@ -73,8 +78,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiCtx& c, const uint32_t (
     v[4] = __uint_as_float(r[8 * g + 4]) + b1.x; v[5] = __uint_as_float(r[8 * g + 5]) + b1.y;
     v[6] = __uint_as_float(r[8 * g + 6]) + b1.z; v[7] = __uint_as_float(r[8 * g + 7]) + b1.w;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
-    if (ep.residual && c.row_ok) {
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act);
+    if (has_res && c.row_ok) {
       const uint32_t w[4] = {rr[g].x, rr[g].y, rr[g].z, rr[g].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -86,7 +91,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiCtx& c, const uint32_t (
     int orow = c.row;                               // global output row
     int srow = c.q * 32 + c.lane;                   // row inside the staged tile
     bool store = c.row_ok;
-    if (ep.gap4) {
+    if (gap4) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
@@ -97,7 +102,23 @@ __device__ __forceinline__ void epilogue_chunk(const EpiCtx& c, const uint32_t (
       srow >>= 2;
       store = c.row_ok && ((c.lane & 3) == 0);
     }
-    if (ep.out_f32) {
+    if (ep.scale_target) {
+      // SE gating: v = gates of clip `row` for 8 channels; scale every pixel of that clip in place
+      if (c.row_ok) {
+        uint16_t* t = static_cast<uint16_t*>(ep.scale_target) + (size_t)c.row * ep.scale_npix * ep.ldo + n0;
+        for (int p = 0; p < ep.scale_npix; ++p, t += ep.ldo) {
+          const uint4 y4 = *reinterpret_cast<const uint4*>(t);
+          const uint32_t w[4] = {y4.x, y4.y, y4.z, y4.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = ptx::unpack_h2(w[j], ep.bf16);
+            o[j] = ptx::pack_h2(f.x * v[2 * j], f.y * v[2 * j + 1], ep.bf16);
+          }
+          *reinterpret_cast<uint4*>(t) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    } else if (ep.out_f32) {
       if (store) {
         float* o = reinterpret_cast<float*>(ep.out) + (size_t)orow * ep.ldo + n0;
         *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
@@ -110,10 +131,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiCtx& c, const uint32_t (
       if (c.staging) {
         // SWIZZLE_128B staging tile: box = 64 columns; 16-byte piece index XORed with (row & 7)
         const int col = c0 + 8 * g;
-        const int rows_box = ep.gap4 ? kGemmBlockM / 4 : kGemmBlockM;
+        const int rows_box = gap4 ? kGemmBlockM / 4 : kGemmBlockM;
         uint8_t* p = c.staging + (size_t)(col >> 6) * rows_box * 128 + (size_t)srow * 128 +
                      ((((col & 63) >> 3) ^ (srow & 7)) << 4);
-        if (!ep.gap4 || (c.lane & 3) == 0) *reinterpret_cast<uint4*>(p) = pk;   // rows past M are clipped by the TMA store
+        if (!gap4 || (c.lane & 3) == 0) *reinterpret_cast<uint4*>(p) = pk;   // rows past M are clipped by the TMA store
       } else if (store) {
         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out) + (size_t)orow * ep.ldo + n0) = pk;
       }
@@ -121,7 +142,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiCtx& c, const uint32_t (
   }
 }
 
-template <int kMinBlocks>
+template <int kMinBlocks, int ACT, int RES, int GAP>
 __global__ void __launch_bounds__(kGemmThreads, kMinBlocks)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmShape sh, const GemmEpilogue ep) {
@@ -251,12 +272,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ptx::tmem_ld_wait();
           const int c1 = c0 + 32;
           if (c1 < n_lim) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c1, rb);
-          epilogue_chunk(ctx, ra, c0);
+          epilogue_chunk<ACT, RES, GAP>(ctx, ra, c0);
           if (c1 >= n_lim) break;
           ptx::tmem_ld_wait();
           c0 = c1 + 32;
           if (c0 < n_lim) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, ra);
-          epilogue_chunk(ctx, rb, c1);
+          epilogue_chunk<ACT, RES, GAP>(ctx, rb, c1);
           if (c0 >= n_lim) break;
         }
       }
@@ -374,7 +395,7 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   // 16-bit outputs go through a swizzled smem tile and TMA stores (full 128-byte lines); fp32 outputs (the final
   // embedding only) and non-dense outputs use direct stores.  Residual reads and the store of one tile touch
   // exactly the same elements, so the in-place skip connection stays race-free.
-  sh.tma_store = (ep.out_f32 || ep.ldo != N) ? 0 : 1;
+  sh.tma_store = (ep.out_f32 || ep.ldo != N || ep.scale_target) ? 0 : 1;
   sh.block_n = block_n > 0 ? block_n : pick_block_n(N, K, sh.m_tiles, sm_count, sh.tma_store != 0);
   KWS_REQUIRE(sh.block_n % 16 == 0 && sh.block_n >= 16 && sh.block_n <= 256, "gemm: bad block_n %d", sh.block_n);
   sh.n_tiles = (N + sh.block_n - 1) / sh.block_n;
@@ -412,19 +433,25 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   // Memory/latency-bound shapes (small K, many tiles): two co-resident CTAs per SM hide each other's TMA, TMEM and
   // store latencies.  Needs half the shared memory and at most 256 TMEM columns per CTA.
   const bool two = smem <= 112 * 1024 && tmem_cols <= 256 && tiles >= 2 * sm_count;
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[two ? 1 : 0]) {
-    if (two) KWS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else KWS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[two ? 1 : 0] = smem;
-  }
-  if (two) {
-    const int grid = tiles < 2 * sm_count ? tiles : 2 * sm_count;
-    gemm_tcgen05_kernel<2><<<grid, kGemmThreads, smem, stream>>>(ta, tb, tout, sh, ep);
-  } else {
-    const int grid = tiles < sm_count ? tiles : sm_count;
-    gemm_tcgen05_kernel<1><<<grid, kGemmThreads, smem, stream>>>(ta, tb, tout, sh, ep);
-  }
+  // compile-time specialised epilogues for the (activation, residual, gap) combinations of the tower; anything else
+  // runs the fully run-time variant
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmShape, const GemmEpilogue);
+  KernelFn k1 = gemm_tcgen05_kernel<1, -1, -1, -1>, k2 = gemm_tcgen05_kernel<2, -1, -1, -1>;
+  const int res = ep.residual ? 1 : 0;
+#define KWS_GEMM_VARIANT(A, R, G) \
+  if (ep.act == A && res == R && ep.gap4 == G) { k1 = gemm_tcgen05_kernel<1, A, R, G>; k2 = gemm_tcgen05_kernel<2, A, R, G>; }
+  KWS_GEMM_VARIANT(kActSwish, 0, 0)
+  KWS_GEMM_VARIANT(kActNone, 0, 0)
+  KWS_GEMM_VARIANT(kActNone, 1, 0)
+  KWS_GEMM_VARIANT(kActRelu, 0, 0)
+  KWS_GEMM_VARIANT(kActSigmoid, 0, 0)
+  KWS_GEMM_VARIANT(kActSwish, 0, 1)
+#undef KWS_GEMM_VARIANT
+  KernelFn kern = two ? k2 : k1;
+  KWS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = two ? 2 : 1;
+  const int grid = tiles < per_sm * sm_count ? tiles : per_sm * sm_count;
+  kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tout, sh, ep);
   KWS_CUDA_CHECK(cudaGetLastError());
   return KWS_OK;
 }

@@ -37,6 +37,10 @@ struct GemmEpilogue {
   int out_f32;                       // 1: store float
   int gap4;                          // 1: average each aligned group of 4 rows -> row m/4
   int bf16;                          // storage/operand type of A, W, residual, 16-bit out: 1 bf16, 0 fp16
+  // SE gating mode: instead of storing the result (the sigmoid gates g[m, n], one row per clip), multiply the
+  // activation tensor scale_target[m, p, n] (p < scale_npix, row pitch ldo) by it in place.
+  void* scale_target;
+  int scale_npix;
 };
 
 struct GemmShape {

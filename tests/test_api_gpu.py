@@ -160,3 +160,20 @@ def test_streaming_matches_per_window_recompute(world, tmp_path):
     assert set(res) == {0.3, 0.9} and all(len(v) == 2 for v in res.values())
     r2, _ = sa.calculate_streaming_accuracy(model, s, flags, existing_inferences=inferences)
     assert r2[0][1] == res
+
+
+def test_host_pipeline_matches_direct_path(world):
+    """EmbedPipeline.run_host (pinned buffers, overlapped copies, sub-batches) == frontend + embedding on the device."""
+    from multilingual_kws_b200.frontend import MicroFrontend
+    from multilingual_kws_b200.model import EmbeddingModel
+    from multilingual_kws_b200.pipeline import EmbedPipeline
+    fe = MicroFrontend()
+    model = EmbeddingModel({k: v for k, v in world["w"].items() if not k.startswith("dense_3")})
+    pcm = torch.from_numpy(world["pcm"])
+    want = model.forward_device(fe.forward(pcm.cuda())).cpu()
+    for sub in (7, 16, 64):
+        pipe = EmbedPipeline(fe, model, n_samples=16000, sub_batch=sub)
+        for _ in range(2):                                     # second call reuses buffers / graphs
+            out = pipe.run_host(pcm.pin_memory())
+            torch.cuda.synchronize()
+            assert torch.equal(out, want)
