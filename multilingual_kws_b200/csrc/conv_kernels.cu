@@ -479,7 +479,41 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
   }
 }
 
+// gating pass of the external-SE path: one CTA per clip (grid-stride), 16-byte vectors
+__global__ void __launch_bounds__(256)
+se_scale_kernel(uint16_t* __restrict__ y, const uint16_t* __restrict__ gates, int batch, int npix, int C, int bf16) {
+  const int C8 = C >> 3, tid = threadIdx.x;
+  const int vec_per_clip = npix * C8;
+  const int step = 256 % C8;
+  for (int clip = blockIdx.x; clip < batch; clip += gridDim.x) {
+    uint4* dst = reinterpret_cast<uint4*>(y) + (size_t)clip * vec_per_clip;
+    const uint4* g = reinterpret_cast<const uint4*>(gates) + (size_t)clip * C8;
+    int c8 = tid % C8;
+    for (int i = tid; i < vec_per_clip; i += 256) {
+      const uint4 v = dst[i];
+      const uint4 gv = __ldg(g + c8);
+      float2 a, b;
+      uint4 o;
+      a = ptx::unpack_h2(v.x, bf16); b = ptx::unpack_h2(gv.x, bf16); o.x = ptx::pack_h2(a.x * b.x, a.y * b.y, bf16);
+      a = ptx::unpack_h2(v.y, bf16); b = ptx::unpack_h2(gv.y, bf16); o.y = ptx::pack_h2(a.x * b.x, a.y * b.y, bf16);
+      a = ptx::unpack_h2(v.z, bf16); b = ptx::unpack_h2(gv.z, bf16); o.z = ptx::pack_h2(a.x * b.x, a.y * b.y, bf16);
+      a = ptx::unpack_h2(v.w, bf16); b = ptx::unpack_h2(gv.w, bf16); o.w = ptx::pack_h2(a.x * b.x, a.y * b.y, bf16);
+      dst[i] = o;
+      c8 += step;
+      if (c8 >= C8) c8 -= C8;
+    }
+  }
+}
+
 }  // namespace
+
+int launch_se_scale(void* d_y, const void* d_gates, int batch, int npix, int C, int bf16, int sm_count, cudaStream_t st) {
+  if (batch == 0) return KWS_OK;
+  const int grid = batch < sm_count * 8 ? batch : sm_count * 8;
+  se_scale_kernel<<<grid, 256, 0, st>>>(static_cast<uint16_t*>(d_y), static_cast<const uint16_t*>(d_gates), batch, npix, C, bf16);
+  KWS_CUDA_CHECK(cudaGetLastError());
+  return KWS_OK;
+}
 
 int launch_stem(const float* d_feats, int batch, const StemParams& P, void* d_out, int sm_count,
                 cudaStream_t st) {

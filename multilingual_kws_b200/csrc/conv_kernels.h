@@ -24,8 +24,7 @@ struct DwseParams {
   const float* b_se2;  // [C]
   // Wide layers: the SE fully-connected pair runs as two batched tensor-core GEMMs over the whole chunk instead of per
   // clip group inside this kernel (the SE weights, up to 442 KB, are then streamed once per chunk, not once per group).
-  // The kernel then stops after the pool: y receives the UN-gated activation, pooled_out [batch, C] the channel means;
-  // the second GEMM's epilogue applies the gates to y in place.
+  // The kernel then stops after the pool: y receives the UN-gated activation, pooled_out [batch, C] the channel means.
   int se_external;
   uint16_t* pooled_out;
 };
@@ -35,5 +34,8 @@ int launch_stem(const float* d_feats, int batch, const StemParams& P, void* d_ou
 int dwse_pick_group(const DwseParams& P, int max_smem, int batch, int sm_count);
 int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int G, int sm_count,
                 cudaStream_t st);
+
+// y[clip, p, c] *= gates[clip, c]   (16-bit, in place; the gating pass of the external-SE path)
+int launch_se_scale(void* d_y, const void* d_gates, int batch, int npix, int C, int bf16, int sm_count, cudaStream_t st);
 
 }  // namespace kws

@@ -505,7 +505,7 @@ extern "C" int kws_embed_launches(const kws_embed_t* m, int batch) {
   const int n_ops = (int)m->ops.size();
   int launches = 0;
   for (int i = 0; i < n_ops; ++i) {
-    const int per = (m->ops[i].kind == kOpDwse && m->ops[i].dw.se_external) ? 3 : 1;   // dw+pool, 2 SE GEMMs (2nd one gates)
+    const int per = (m->ops[i].kind == kOpDwse && m->ops[i].dw.se_external) ? 4 : 1;   // dw+pool, 2 SE GEMMs, gating
     launches += per * (i < m->split_op ? (batch + ce - 1) / ce : (batch + cl - 1) / cl);
   }
   return launches;
@@ -638,11 +638,12 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
             rc = gemm_h16(se_pooled, op.se_w1, nb, op.se_pad, P.C, 0, e1, m->sm_count, st);
             if (rc == KWS_OK) {
               GemmEpilogue e2 = e1;
-              // expand FC + sigmoid; its epilogue applies the gates to the activation in place (no gates tensor, no extra pass)
+              // (an epilogue that applies the gates in place — GemmEpilogue::scale_target — measured slower than the
+              //  separate coalesced gating pass: one thread per clip walks the pixels with a 2*C-byte stride)
               e2.bias = P.b_se2; e2.out = se_gates; e2.ldo = P.C; e2.ldr = P.C; e2.act = kActSigmoid;
-              e2.scale_target = out_ptr; e2.scale_npix = P.Ho * P.Wo;
               rc = gemm_h16(se_squeeze, op.se_w2, nb, P.C, op.se_pad, 0, e2, m->sm_count, st);
             }
+            if (rc == KWS_OK) rc = launch_se_scale(out_ptr, se_gates, nb, P.Ho * P.Wo, P.C, m->bf16, m->sm_count, st);
           }
         } else {
           GemmEpilogue ep;
