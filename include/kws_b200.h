@@ -33,6 +33,13 @@ typedef struct kws_head kws_head_t;
 const char* kws_last_error(void);
 int kws_abi_version(void);
 
+/* Page-locked host staging memory for callers that hold their clips in HOST buffers (the reference feeds numpy
+ * arrays: multilingual_kws/embedding/input_data.py:66-83 file2spec, batch_streaming_analysis.py:100-118).
+ * write_combined = 1 -> cudaHostAllocWriteCombined: upload-only buffers (the host writes PCM into them, the device
+ * reads them over PCIe at line rate); 0 -> ordinary pinned memory (download buffers the host reads). */
+int kws_host_alloc(void** out, size_t bytes, int write_combined);
+int kws_host_free(void* p);
+
 /* ---------------------------------------------------------------------------------------------
  * Frontend — replaces frontend_op.audio_microfrontend(...) as called at
  * multilingual_kws/embedding/input_data.py:25-33 (and its per-window use at

@@ -18,6 +18,8 @@ c_void_p, c_int, c_float, c_size_t, c_int64 = ctypes.c_void_p, ctypes.c_int, cty
 SIGNATURES = {
     "kws_last_error": (ctypes.c_char_p, []),
     "kws_abi_version": (c_int, []),
+    "kws_host_alloc": (c_int, [ctypes.POINTER(c_void_p), c_size_t, c_int]),
+    "kws_host_free": (c_int, [c_void_p]),
     "kws_frontend_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                                     c_float, c_float, c_float, c_int, c_float, c_float, c_int, c_int, c_int]),
     "kws_frontend_destroy": (None, [c_void_p]),

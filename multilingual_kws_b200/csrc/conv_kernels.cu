@@ -47,6 +47,8 @@ stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, uint1
     for (int j = 0; j < 8; ++j) wr[t][j] = s_w[t * kStemC + g * 8 + j];
 #pragma unroll
   for (int j = 0; j < 8; ++j) br[j] = s_b[g * 8 + j];
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   for (int clip = blockIdx.x; clip < batch; clip += gridDim.x) {
     __syncthreads();
     const float* src = feats + (size_t)clip * P.H * P.W;
@@ -232,6 +234,8 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
     ptx::fence_barrier_init();
   }
   __syncthreads();
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();              // weights / barrier set-up above overlapped the predecessor's tail
 
   // thread -> (channel pair, pixel lane)
   const int PL = L.PL;
@@ -485,6 +489,8 @@ se_scale_kernel(uint16_t* __restrict__ y, const uint16_t* __restrict__ gates, in
   const int C8 = C >> 3, tid = threadIdx.x;
   const int vec_per_clip = npix * C8;
   const int step = 256 % C8;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   for (int clip = blockIdx.x; clip < batch; clip += gridDim.x) {
     uint4* dst = reinterpret_cast<uint4*>(y) + (size_t)clip * vec_per_clip;
     const uint4* g = reinterpret_cast<const uint4*>(gates) + (size_t)clip * C8;
@@ -510,8 +516,8 @@ se_scale_kernel(uint16_t* __restrict__ y, const uint16_t* __restrict__ gates, in
 int launch_se_scale(void* d_y, const void* d_gates, int batch, int npix, int C, int bf16, int sm_count, cudaStream_t st) {
   if (batch == 0) return KWS_OK;
   const int grid = batch < sm_count * 8 ? batch : sm_count * 8;
-  se_scale_kernel<<<grid, 256, 0, st>>>(static_cast<uint16_t*>(d_y), static_cast<const uint16_t*>(d_gates), batch, npix, C, bf16);
-  KWS_CUDA_CHECK(cudaGetLastError());
+  KWS_CUDA_CHECK(launch_pdl(se_scale_kernel, dim3(grid), dim3(256), 0, st, static_cast<uint16_t*>(d_y),
+                            static_cast<const uint16_t*>(d_gates), batch, npix, C, bf16));
   return KWS_OK;
 }
 
@@ -520,7 +526,8 @@ int launch_stem(const float* d_feats, int batch, const StemParams& P, void* d_ou
   if (batch == 0) return KWS_OK;
   const size_t smem = (size_t)(((P.H * P.W + 3) & ~3) + 9 * kStemC + kStemC) * 4;
   const int grid = batch < sm_count * 4 ? batch : sm_count * 4;
-  stem_conv_kernel<<<grid, kStemThreads, smem, st>>>(d_feats, batch, P, static_cast<uint16_t*>(d_out));
+  KWS_CUDA_CHECK(launch_pdl(stem_conv_kernel, dim3(grid), dim3(kStemThreads), smem, st, d_feats, batch, P,
+                            static_cast<uint16_t*>(d_out)));
   KWS_CUDA_CHECK(cudaGetLastError());
   return KWS_OK;
 }
@@ -565,8 +572,8 @@ int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int 
   const int n_groups = (batch + G - 1) / G;
   const int per_sm = smem <= 100 * 1024 ? 2 : 1;
   const int grid = n_groups < sm_count * per_sm ? n_groups : sm_count * per_sm;
-  kern<<<grid, kDwThreads, smem, st>>>(static_cast<const uint16_t*>(d_x), batch, G, P, static_cast<uint16_t*>(d_y));
-  KWS_CUDA_CHECK(cudaGetLastError());
+  KWS_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kDwThreads), smem, st, static_cast<const uint16_t*>(d_x), batch, G, P,
+                            static_cast<uint16_t*>(d_y)));
   return KWS_OK;
 }
 

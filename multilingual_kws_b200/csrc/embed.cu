@@ -178,6 +178,12 @@ struct Builder {
       }
     return upload(m, h, &cerr);
   }
+  // same, from a host fp32 [N][K] matrix (used for folded projection -> expansion pairs)
+  const uint16_t* gemm_weight_host(const std::vector<double>& wnk) {
+    std::vector<uint16_t> h(wnk.size());
+    for (size_t i = 0; i < wnk.size(); ++i) h[i] = h16((float)wnk[i]);
+    return upload(m, h, &cerr);
+  }
   const float* vec(const std::vector<float>& v) { return upload(m, v, &cerr); }
   uint16_t h16(float v) const {
     uint16_t bits;
@@ -259,6 +265,14 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
     m->ops.push_back(op);
   }
   // ---- MBConv blocks
+  // A projection without a skip connection whose only consumer is the next block's expansion (also without a
+  // skip from that tensor) is a linear map followed by a linear map: W_e (W_p d + b_p) + b_e.  The pair is folded
+  // into one GEMM (K = the projection's input channels) and the narrow tensor in between never exists.  With the
+  // Keras B0 configuration this is block1a's projection into block2a's expansion (32 -> 16 -> 96 becomes 32 -> 96).
+  const bool fold_linear_pairs = !(getenv("KWS_NO_FOLD") && atoi(getenv("KWS_NO_FOLD")));
+  std::vector<double> pend_w;          // pending projection [cout][cexp], BN scale applied
+  std::vector<double> pend_b;          // its shift [cout]
+  int pend_k = 0;                      // its input channels (0: nothing pending)
   for (int si = 0; si < 7; ++si) {
     for (int r = 0; r < kStages[si].reps; ++r) {
       const BlockCfg& c = kStages[si];
@@ -273,11 +287,29 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
         Op op;
         op.kind = kOpGemm; op.name = n + "_expand_activation"; op.in_buf = 0; op.out_buf = 1;
         op.rows_per_clip = h * w; op.N = cexp; op.K = cin; op.act = kActSwish;
-        op.w = B.gemm_weight(n + "_expand_conv/kernel", cin, cexp, &sc);
+        if (pend_k) {
+          const HostTensor* ke = B.get(n + "_expand_conv/kernel", (size_t)cin * cexp);
+          CK(ke);
+          std::vector<double> wf((size_t)cexp * pend_k, 0.0);
+          for (int o = 0; o < cexp; ++o) {
+            double bacc = sh[o];
+            for (int j = 0; j < cin; ++j) {
+              const double we = (double)ke->data[(size_t)j * cexp + o] * sc[o];
+              bacc += we * pend_b[j];
+              for (int q = 0; q < pend_k; ++q) wf[(size_t)o * pend_k + q] += we * pend_w[(size_t)j * pend_k + q];
+            }
+            sh[o] = (float)bacc;
+          }
+          op.in_buf = 2; op.K = pend_k;
+          op.w = B.gemm_weight_host(wf);
+          pend_k = 0;
+        } else {
+          op.w = B.gemm_weight(n + "_expand_conv/kernel", cin, cexp, &sc);
+        }
         op.bias = B.vec(sh);
         CK(op.w && op.bias);
         op.out_elems_per_clip = (size_t)h * w * cexp;
-        macs += (double)h * w * cin * cexp;
+        macs += (double)h * w * op.K * cexp;
         m->ops.push_back(op);
       }
       {
@@ -340,6 +372,20 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
       {
         std::vector<float> sc, sh;
         CK(B.bn(n + "_project_bn", cout, &sc, &sh));
+        const bool has_skip = stride == 1 && cin == cout;
+        const bool last_rep = r + 1 == kStages[si].reps;
+        if (fold_linear_pairs && !has_skip && last_rep && si + 1 < 7 && kStages[si + 1].e != 1 &&
+            !(kStages[si + 1].s == 1 && kStages[si + 1].fin == kStages[si + 1].fout)) {
+          const HostTensor* kp = B.get(n + "_project_conv/kernel", (size_t)cexp * cout);
+          CK(kp);
+          pend_w.assign((size_t)cout * cexp, 0.0); pend_b.assign(cout, 0.0);
+          for (int o = 0; o < cout; ++o) {
+            pend_b[o] = sh[o];
+            for (int q = 0; q < cexp; ++q) pend_w[(size_t)o * cexp + q] = (double)kp->data[(size_t)q * cout + o] * sc[o];
+          }
+          pend_k = cexp;
+          continue;
+        }
         Op op;
         op.kind = kOpGemm; op.name = n + "_out"; op.in_buf = 2; op.out_buf = 0;
         op.rows_per_clip = h * w; op.N = cout; op.K = cexp; op.act = kActNone;

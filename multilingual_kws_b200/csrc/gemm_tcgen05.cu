@@ -191,6 +191,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();              // the set-up above overlapped the predecessor's tail; operands are valid from here
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -451,8 +453,7 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   KWS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = two ? 2 : 1;
   const int grid = tiles < per_sm * sm_count ? tiles : per_sm * sm_count;
-  kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tout, sh, ep);
-  KWS_CUDA_CHECK(cudaGetLastError());
+  KWS_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, stream, ta, tb, tout, sh, ep));
   return KWS_OK;
 }
 

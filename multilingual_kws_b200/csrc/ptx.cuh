@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace kws {
 namespace ptx {
@@ -23,6 +24,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may begin while its
+// predecessor on the stream is still running; pdl_wait() blocks until the predecessor grid has completed and its
+// writes are visible, pdl_launch_dependents() lets the successor's CTAs be scheduled once every CTA of this grid has
+// issued it (or exited).  Everything before pdl_wait() must touch only constants (weights, tensor maps, barriers).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -155,4 +163,23 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t w, int bf) {
 }
 
 }  // namespace ptx
+
+// Launch with programmatic stream serialization (see ptx::pdl_wait).  Every kernel launched through this helper
+// executes ptx::pdl_wait() on all of its threads before it reads activations or writes anything.  KWS_NO_PDL=1
+// turns the attribute off (plain stream order) for A/B measurements.
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("KWS_NO_PDL"); return !(e && atoi(e)); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 }  // namespace kws

@@ -177,3 +177,37 @@ def test_host_pipeline_matches_direct_path(world):
             out = pipe.run_host(pcm.pin_memory())
             torch.cuda.synchronize()
             assert torch.equal(out, want)
+
+
+def test_host_pipeline_back_to_back_calls(world):
+    """run_host only enqueues: several calls in flight (slots recycled across calls, no host sync in between) must
+    each deliver their own rows; join() orders the caller's stream after the last download."""
+    from multilingual_kws_b200.frontend import MicroFrontend
+    from multilingual_kws_b200.model import EmbeddingModel
+    from multilingual_kws_b200.pipeline import EmbedPipeline
+    fe = MicroFrontend()
+    model = EmbeddingModel({k: v for k, v in world["w"].items() if not k.startswith("dense_3")})
+    pcm = torch.from_numpy(world["pcm"])
+    n = pcm.shape[0]
+    inputs = [torch.roll(pcm, shifts=i, dims=0).contiguous() for i in range(7)]
+    want = [model.forward_device(fe.forward(x.cuda())).cpu() for x in inputs]
+    pinned = [x.pin_memory() for x in inputs]
+    for sub, depth in ((n, 2), (n, 3), (max(1, n // 3), 3)):
+        pipe = EmbedPipeline(fe, model, n_samples=16000, sub_batch=sub, depth=depth)
+        if depth == 3:                                          # write-combined upload buffers from the C ABI
+            pinned = [pipe.alloc_input(n) for _ in inputs]
+            for dst, src in zip(pinned, inputs):
+                dst.copy_(src)
+                assert dst.is_pinned() and dst.shape == src.shape and dst.dtype == torch.int16
+        outs = [pipe.run_host(x) for x in pinned]
+        pipe.join()
+        done = torch.cuda.Event()
+        done.record()
+        done.synchronize()
+        for o, w_ in zip(outs, want):
+            assert torch.equal(o, w_)
+        outs = [pipe.run_host(x) for x in pinned[:2]]
+        pipe.synchronize()
+        assert torch.equal(outs[0], want[0]) and torch.equal(outs[1], want[1])
+    with pytest.raises(ValueError):
+        pipe.run_host(torch.zeros((2, 100), dtype=torch.int16).pin_memory())
