@@ -19,8 +19,15 @@ namespace kws {
 
 namespace {
 
-__device__ __forceinline__ float swish(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid(x) = 0.5 tanh(x/2) + 0.5 with the hardware tanh: one MUFU op and three instructions per swish instead of
+// EX2 + RCP and five (the same form the GEMM epilogues use; the result is rounded to 16 bits anyway)
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float swish(float x) { const float h = 0.5f * x; return fmaf(h, tanh_approx(h), h); }
+__device__ __forceinline__ float sigmoidf(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
 // ---------------------------------------------------------------- stem
 constexpr int kStemThreads = 256;
@@ -88,8 +95,10 @@ constexpr int kDwThreads = 256;
 
 struct DwSmem {
   uint32_t in_bytes, out_off, pooled_off, part_off, s_off, red_off, bar_off, w_off, w_floats, total;
+  uint32_t in2_off;   // second input buffer (0: single-buffered)
   int PL;   // pixel lanes per channel pair
 };
+constexpr uint32_t kDwSmemCap = 227 * 1024;
 __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
   DwSmem L;
   const int C2 = P.C >> 1;
@@ -107,6 +116,15 @@ __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
   L.w_off = (L.bar_off + 16 + 15) & ~15u;
   if (L.w_floats * 4 > 40 * 1024) L.w_floats = 0;
   L.total = L.w_off + L.w_floats * 4;
+  // A layer whose group does not leave room for a second CTA on the SM (block2a: 96 KB of input per clip) would
+  // expose the whole bulk-load latency of every group; if two input buffers fit, the next group's load is issued
+  // while the current one is convolved.
+  L.in2_off = 0;
+  const uint32_t in2 = (L.total + 127) & ~127u;
+  if (L.total > 100 * 1024 && in2 + L.in_bytes <= kDwSmemCap) {
+    L.in2_off = in2;
+    L.total = in2 + L.in_bytes;
+  }
   return L;
 }
 
@@ -200,6 +218,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
   extern __shared__ __align__(128) uint8_t smem[];
   const DwSmem L = dw_smem(P, G);
   const uint32_t* s_in = reinterpret_cast<const uint32_t*>(smem);              // bf16x2 words, [G][H][W][C/2]
+  const bool two_in = L.in2_off != 0;
   uint32_t* s_out = reinterpret_cast<uint32_t*>(smem + L.out_off);            // bf16x2, [G][Ho*Wo][C/2]
   float* s_pool = reinterpret_cast<float*>(smem + L.pooled_off);              // [G][C] sums, later gates
   float* s_part = reinterpret_cast<float*>(smem + L.part_off);                // [PL][G][C] (deterministic pool reduce)
@@ -231,6 +250,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
   }
   if (tid == 0) {
     ptx::mbar_init(bar, 1);
+    ptx::mbar_init(bar + 1, 1);
     ptx::fence_barrier_init();
   }
   __syncthreads();
@@ -242,20 +262,25 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
   const int cp0 = C2 >= kDwThreads ? tid : tid % C2;
   const int pl = C2 >= kDwThreads ? 0 : tid / C2;
   const bool active = pl < PL;
-  uint32_t parity = 0;
-
   const int n_groups = (batch + G - 1) / G;
-  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+  auto issue_load = [&](int grp_, int buf) {                 // one thread: bulk copy of a whole group into buffer `buf`
+    const int g0_ = grp_ * G;
+    const uint32_t bytes = (uint32_t)min(G, batch - g0_) * clip_words * 4;
+    ptx::mbar_expect_tx(bar + buf, bytes);
+    ptx::tma_bulk_g2s(smem + (buf ? L.in2_off : 0u), x + (size_t)g0_ * clip_words * 2, bytes, bar + buf);
+  };
+  if (two_in && tid == 0 && (int)blockIdx.x < n_groups) issue_load(blockIdx.x, 0);
+  int it = 0;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++it) {
     const int g0 = grp * G;
     const int gn = min(G, batch - g0);
-    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)gn * clip_words * 4;
-      ptx::mbar_expect_tx(bar, bytes);
-      ptx::tma_bulk_g2s(smem, x + (size_t)g0 * clip_words * 2, bytes, bar);
-    }
-    ptx::mbar_wait(bar, parity);
-    parity ^= 1;
+    const int cur = two_in ? (it & 1) : 0;
+    if (!two_in && tid == 0) issue_load(grp, 0);
+    ptx::mbar_wait(bar + cur, two_in ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u));
     __syncthreads();
+    // the other buffer was last read by the previous group's convolution, which every thread has left
+    if (two_in && tid == 0 && grp + (int)gridDim.x < n_groups) issue_load(grp + gridDim.x, cur ^ 1);
+    s_in = reinterpret_cast<const uint32_t*>(smem + (cur ? L.in2_off : 0u));
 
     // ---- depthwise conv + BN + swish -> s_out (16-bit), channel sums -> s_pool
     if constexpr (GEOM >= 1 && GEOM <= 6) {
@@ -571,6 +596,7 @@ int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int 
   KWS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_groups = (batch + G - 1) / G;
   const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+  KWS_REQUIRE(smem <= (size_t)kDwSmemCap, "dwse: %zu bytes of shared memory exceed the per-CTA limit", smem);
   const int grid = n_groups < sm_count * per_sm ? n_groups : sm_count * per_sm;
   KWS_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kDwThreads), smem, st, static_cast<const uint16_t*>(d_x), batch, G, P,
                             static_cast<uint16_t*>(d_y)));

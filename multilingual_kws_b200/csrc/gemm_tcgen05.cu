@@ -164,8 +164,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_kb = (sh.K + sh.block_k - 1) / sh.block_k;
   const int k16_total = (sh.K + 15) / 16;
   const int total_tiles = sh.m_tiles * sh.n_tiles;
+  const int acc_stages = sh.acc_stages;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * (uint32_t)block_n) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(acc_stages * block_n)) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmap_a);
@@ -238,8 +239,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         ptx::tc_commit(tmem_full + acc);                  // accumulator complete
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
       }
     }
     __syncwarp();
@@ -250,12 +250,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int et = (int)threadIdx.x - 64;                 // 0..255 among epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
+    int bias_buf = 0;
+    const bool bias_once = sh.n_tiles == 1;               // one column tile: the bias slice is the same for every tile
+    if (bias_once && et < block_n) s_bias[et] = (ep.bias && et < sh.N) ? __ldg(ep.bias + et) : 0.0f;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_t = tile / sh.n_tiles, n_t = tile - m_t * sh.n_tiles;
-      float* sb = s_bias + acc * 256;
-      if (et < block_n) {
-        const int n = n_t * block_n + et;
-        sb[et] = (ep.bias && n < sh.N) ? __ldg(ep.bias + n) : 0.0f;
+      // per-tile slices alternate between two buffers: a warp that is already on tile i+1 writes the other buffer
+      // than the one laggards of tile i still read (the barrier below orders the reuse two tiles later)
+      float* sb = s_bias + bias_buf * 256;
+      if (!bias_once) {
+        if (et < block_n) {
+          const int n = n_t * block_n + et;
+          sb[et] = (ep.bias && n < sh.N) ? __ldg(ep.bias + n) : 0.0f;
+        }
+        bias_buf ^= 1;
       }
       if (staging && et == 0) ptx::tma_store_wait_read();  // previous tile's TMA stores have drained the staging tile
       asm volatile("bar.sync 1, 256;" ::: "memory");       // epilogue warps only
@@ -297,8 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ptx::tma_store_commit();
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
     }
     if (staging && et == 0) ptx::tma_store_wait_all();     // global writes complete before the kernel exits
   }
@@ -408,7 +415,13 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   const int tiles_per_cta = (sh.m_tiles * sh.n_tiles + sm_count - 1) / sm_count;
   // Stage count = how many k-blocks (for single-k-block layers: how many TILES) may be in flight per CTA.  Memory-
   // bound small-K layers want as many as fit in ~half the SM's shared memory (so two CTAs co-reside).
-  const size_t budget = (num_kb <= 2 && sh.block_n <= 128) ? 110 * 1024 : 220 * 1024;
+  // Many-tile problems (the early layers: M = 10^5 rows, small K and N) are bound by the per-tile latency chain
+  // (TMEM load -> epilogue math -> staging -> TMA store), not by operand bandwidth: they run two CTAs per SM, each
+  // with half the shared memory and 256 TMEM columns (one accumulator stage when block_n > 128).
+  const int tiles_total = sh.m_tiles * sh.n_tiles;
+  const bool many_tiles = tiles_total >= 2 * sm_count;
+  const size_t budget = ((num_kb <= 2 && sh.block_n <= 128) || (many_tiles && num_kb <= 4)) ? 110 * 1024 : 220 * 1024;
+  sh.acc_stages = 2;
   int stages = kGemmMaxStages;
   while (stages > 2 && smem_layout(sh.block_n, sh.block_k, stages, staging_rows).total + 1024 > budget) --stages;
   const int useful = num_kb * (tiles_per_cta < 8 ? tiles_per_cta : 8) + 1;
@@ -430,11 +443,10 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
     tout = ta;   // unused
   }
   const int tiles = sh.m_tiles * sh.n_tiles;
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * (uint32_t)sh.block_n) tmem_cols <<= 1;
   // Memory/latency-bound shapes (small K, many tiles): two co-resident CTAs per SM hide each other's TMA, TMEM and
   // store latencies.  Needs half the shared memory and at most 256 TMEM columns per CTA.
-  const bool two = smem <= 112 * 1024 && tmem_cols <= 256 && tiles >= 2 * sm_count;
+  const bool two = smem <= 112 * 1024 && tiles >= 2 * sm_count;
+  if (two && sh.block_n > 128) sh.acc_stages = 1;
   // compile-time specialised epilogues for the (activation, residual, gap) combinations of the tower; anything else
   // runs the fully run-time variant
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmShape, const GemmEpilogue);

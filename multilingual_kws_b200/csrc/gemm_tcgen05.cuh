@@ -51,6 +51,8 @@ struct GemmShape {
                                      // get narrow tiles, so many more of them fit in flight (memory-level parallelism)
   int m_tiles, n_tiles;
   int tma_store;                     // 1: epilogue stages the tile in swizzled smem and writes it with TMA stores
+  int acc_stages;                    // TMEM accumulator stages per CTA: 2, or 1 for wide tiles (block_n > 128) that
+                                     // should still leave room for a second CTA on the SM (256 of the 512 columns)
 };
 
 // Host: build the tensor maps, pick the tile shape (block_n = 0 -> cost model) and launch on `stream`.

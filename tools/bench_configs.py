@@ -1,0 +1,146 @@
+"""Measurements of the BASELINE.json configurations that are not bench.py's headline line:
+
+  cfg1  log-mel frontend only, B = 32 (and the large-batch asymptote of the same kernel)
+  cfg2  batch sweep of frontend + embedding forward (B = 32 ... 16384): the launch/latency-bound -> throughput asymptote
+  cfg3  5-shot 3-way head fine-tune, batch 512, 100 steps (embedding forward + head fwd/bwd + Adam per step)
+  cfg5  streaming: 30 min of synthetic 16 kHz audio, 1 s window / 100 ms hop; offline windows/s (frame-reuse frontend,
+        batched embedding + head) and the p50 / p99 latency of one online hop (newest window only, result on the host)
+
+CUDA-event timing with an L2 flush between iterations for the throughput numbers, wall clock with a full
+synchronisation for latencies.  Prints one JSON object; `python tools/bench_configs.py > gpurun_out/r01_configs.json`."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from multilingual_kws_b200 import weights as W
+from multilingual_kws_b200.embedding.transfer_learning import train_step
+from multilingual_kws_b200.fewshot import FewShotModel, Head
+from multilingual_kws_b200.frontend import FEATURE_SCALE, MicroFrontend
+from multilingual_kws_b200.model import EmbeddingModel
+from multilingual_kws_b200.synthetic import synthetic_pcm, synthetic_stream
+
+dev = torch.device("cuda", 0)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+fe = MicroFrontend()
+w = W.random_init(0, randomize_bn=True, residual_gamma_scale=0.3)
+model = EmbeddingModel(w)
+res = {"device": torch.cuda.get_device_name(0)}
+
+
+def event_ms(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    return float(np.median(ts))
+
+
+def pcm_batch(B, cfg_id):
+    base = synthetic_pcm(min(B, 256), cfg_id=cfg_id)
+    return torch.from_numpy(np.tile(base, (-(-B // base.shape[0]), 1))[:B]).to(dev)
+
+
+# ---- cfg1 + asymptote: frontend only
+rows = []
+for B in (32, 1024, 8192, 32768):
+    pcm = pcm_batch(B, 1)
+    out = torch.empty((B, 49, 40), dtype=torch.float32, device=dev)
+    ms = event_ms(lambda: fe.forward(pcm, out=out))
+    rows.append({"batch": B, "ms": round(ms, 4), "clips_per_s": round(B / ms * 1e3), "algorithmic_GBps": round(B * 39840 / ms / 1e6, 1)})
+res["cfg1_frontend_only"] = rows
+
+# ---- cfg2 sweep: frontend + embedding forward
+rows = []
+for B in (32, 128, 512, 1024, 2048, 4096, 8192, 16384):
+    pcm = pcm_batch(B, 2)
+    feats = torch.empty((B, 49, 40), dtype=torch.float32, device=dev)
+    emb = torch.empty((B, model.output_dim), dtype=torch.float32, device=dev)
+
+    def step():
+        fe.forward(pcm, out=feats)
+        model.forward_device(feats, out=emb)
+    ms = event_ms(step)
+    rows.append({"batch": B, "ms": round(ms, 4), "utt_per_s": round(B / ms * 1e3), "launches": 1 + model.launches(B)})
+res["cfg2_batch_sweep_frontend_plus_embedding"] = rows
+
+# ---- cfg3: 100 fine-tune steps, batch 512
+B = 512
+feats = fe.forward(pcm_batch(B, 3))
+labels = torch.from_numpy(np.random.default_rng(1234 + 3).integers(0, 3, B).astype(np.int32)).to(dev)
+ft = FewShotModel(model, Head.keras_init(model.output_dim, 18, 3, seed=0))
+for _ in range(5):
+    train_step(ft, feats, labels, 1e-3)
+ft.head.reset_optimizer()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+losses = [train_step(ft, feats, labels, 1e-3)[0] for _ in range(100)]
+torch.cuda.synchronize()
+wall = time.perf_counter() - t0
+res["cfg3_finetune_100_steps_batch512"] = {
+    "wall_s": round(wall, 4), "ms_per_step": round(wall * 10, 4), "utt_per_s": round(100 * B / wall),
+    "loss_first": round(losses[0], 5), "loss_last": round(losses[-1], 5),
+    "note": "each step: embedding forward (frozen) + head fwd/bwd + Adam; train_step returns loss/accuracy to the host "
+            "(one D2H sync per step, as Keras' fit loop does for its progress bar)"}
+
+# ---- cfg5: streaming
+n = 30 * 60 * 16000
+audio = torch.from_numpy(synthetic_stream(n, cfg_id=5)).to(dev)
+clip, hop = 16000, 1600
+Wn = fe.stream_num_windows(n, clip, hop)
+torch.cuda.synchronize()
+
+
+def offline(batch):
+    st = fe.stream_prepare(audio)
+    outs = []
+    for w0 in range(0, Wn, batch):
+        outs.append(ft.forward_device(st.windows(clip, hop, w0, min(batch, Wn - w0), FEATURE_SCALE)))
+    return outs
+
+
+for _ in range(2):
+    offline(4096)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+probs = torch.cat(offline(4096)).cpu()
+wall = time.perf_counter() - t0
+res["cfg5_streaming_offline"] = {
+    "audio_s": n / 16000, "windows": int(Wn), "window_batch": 4096, "wall_s": round(wall, 4),
+    "windows_per_s": round(Wn / wall), "realtime_factor": round(n / 16000 / wall),
+    "note": "PCM resident on the device; per-frame magnitudes computed once (frame reuse), softmax rows copied to the host"}
+
+# online: audio arrives hop by hop; per hop the newest 1 s window goes through frontend + embedding + head and its
+# softmax row is read on the host.  The per-frame magnitudes are already there for all but the newest 5 frames; the
+# stream state is prepared once, so each call is the window-tail kernel + B = 1 embedding graph + head + 12-byte D2H.
+st = fe.stream_prepare(audio)
+st.windows(clip, hop, 0, 1, FEATURE_SCALE)
+lat = []
+for i in range(1, 501):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    p = ft.forward_device(st.windows(clip, hop, i, 1, FEATURE_SCALE)).cpu()
+    lat.append((time.perf_counter() - t0) * 1e3)
+lat = np.array(lat[50:])
+res["cfg5_streaming_online_one_window_per_hop"] = {
+    "p50_ms": round(float(np.percentile(lat, 50)), 4), "p99_ms": round(float(np.percentile(lat, 99)), 4),
+    "hops": int(lat.size), "hop_ms": 100,
+    "note": "wall clock around frontend window + embedding (B = 1) + head + D2H of the softmax row"}
+lat = []
+for i in range(0, 200):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    p = ft.forward_device(st.windows(clip, hop, 10 * i, 10, FEATURE_SCALE)).cpu()
+    lat.append((time.perf_counter() - t0) * 1e3)
+lat = np.array(lat[20:])
+res["cfg5_streaming_online_ten_windows_per_second"] = {
+    "p50_ms": round(float(np.percentile(lat, 50)), 4), "p99_ms": round(float(np.percentile(lat, 99)), 4), "calls": int(lat.size)}
+print(json.dumps(res, indent=1))
