@@ -680,12 +680,12 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
           if (rc == KWS_OK && P.se_external) {
             GemmEpilogue e1;
             e1.bias = op.se_b1; e1.residual = nullptr; e1.out = se_squeeze; e1.ldo = op.se_pad; e1.ldr = op.se_pad;
-            e1.act = kActSwish; e1.out_f32 = 0; e1.gap4 = 0; e1.bf16 = m->bf16; e1.scale_target = nullptr; e1.scale_npix = 0;
+            e1.act = kActSwish; e1.out_f32 = 0; e1.gap4 = 0; e1.bf16 = m->bf16;
             rc = gemm_h16(se_pooled, op.se_w1, nb, op.se_pad, P.C, 0, e1, m->sm_count, st);
             if (rc == KWS_OK) {
               GemmEpilogue e2 = e1;
-              // (an epilogue that applies the gates in place — GemmEpilogue::scale_target — measured slower than the
-              //  separate coalesced gating pass: one thread per clip walks the pixels with a 2*C-byte stride)
+              // (applying the gates inside this epilogue measured slower than the separate coalesced gating pass:
+              //  one thread per clip would walk the pixels with a 2*C-byte stride)
               e2.bias = P.b_se2; e2.out = se_gates; e2.ldo = P.C; e2.ldr = P.C; e2.act = kActSigmoid;
               rc = gemm_h16(se_squeeze, op.se_w2, nb, P.C, op.se_pad, 0, e2, m->sm_count, st);
             }
@@ -697,7 +697,6 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
           ep.residual = op.res_buf >= 0 ? bufs[op.res_buf] : nullptr;
           ep.out = out_ptr; ep.ldo = op.N; ep.ldr = op.N;
           ep.act = op.act; ep.out_f32 = op.out_f32; ep.gap4 = op.gap4; ep.bf16 = m->bf16;
-          ep.scale_target = nullptr; ep.scale_npix = 0;
           rc = gemm_h16(bufs[op.in_buf], op.w, op.rows_per_clip * nb, op.N, op.K, 0, ep, m->sm_count, st);
         }
         if (rc != KWS_OK) return rc;
@@ -753,6 +752,5 @@ extern "C" int kws_gemm_h16(const void* d_a, const void* d_w, int M, int N, int 
   GemmEpilogue ep;
   ep.bias = d_bias; ep.residual = d_residual;
   ep.out = d_out; ep.ldo = N; ep.ldr = N; ep.act = act; ep.out_f32 = out_f32; ep.gap4 = gap4; ep.bf16 = dtype;
-  ep.scale_target = nullptr; ep.scale_npix = 0;
   return gemm_h16(d_a, d_w, M, N, K, block_n, ep, sm, (cudaStream_t)stream);
 }

@@ -12,17 +12,13 @@ namespace {
 
 
 struct SmemLayout {
-  uint32_t stage_bytes, staging_off, staging_bytes, bar_off, bias_off, total;
+  uint32_t stage_bytes, bar_off, total;
 };
-// staging: the output tile in TMA-store layout: ceil(block_n / 64) boxes of [rows_box][64] 16-bit, SWIZZLE_128B
-__host__ __device__ inline SmemLayout smem_layout(int block_n, int block_k, int stages, int staging_rows) {
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int block_k, int stages) {
   SmemLayout L;
   L.stage_bytes = (uint32_t)(kGemmBlockM + block_n) * block_k * 2;     // A tile then W tile, both multiples of 512 B
-  L.staging_off = (L.stage_bytes * stages + 1023) & ~1023u;
-  L.staging_bytes = (uint32_t)((block_n + 63) / 64) * staging_rows * 128;
-  L.bar_off = L.staging_off + L.staging_bytes;
-  L.bias_off = L.bar_off + 8 * (2 * kGemmMaxStages + 4) + 16;          // float s_bias[2][256]
-  L.total = L.bias_off + 2 * 256 * 4;
+  L.bar_off = (L.stage_bytes * stages + 1023) & ~1023u;
+  L.total = L.bar_off + 8 * (2 * kGemmMaxStages + 4) + 16;
   return L;
 }
 
@@ -40,124 +36,110 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-struct EpiCtx {
-  const GemmShape& sh;
-  const GemmEpilogue& ep;
-  const float* sb;          // this tile's bias slice in smem
-  uint8_t* staging;         // nullptr -> direct global stores
-  int n_t, row, lane, q;
-  bool row_ok;
-};
+// 256-bit global accesses (one full 32-byte sector per thread and instruction)
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 
-// One 16-column chunk of one accumulator row: bias, activation, residual, optional 4-row mean, store.
-// ACT / RES / GAP are compile-time for the configurations the embedding tower uses (-1 = read from `ep` at run time).
-template <int ACT, int RES, int GAP>
-__device__ __forceinline__ void epilogue_chunk(const EpiCtx& c, const uint32_t (&r)[16], int c0) {
-  const GemmShape& sh = c.sh;
-  const GemmEpilogue& ep = c.ep;
+// One 16-column chunk of one accumulator row (this thread's row, columns n0 .. n0+15 of the output): bias, activation,
+// residual, optional 4-row mean, store.  Every thread owns 32 contiguous output bytes (64 for fp32), so the chunk is
+// written by one 256-bit store per thread: full sectors, no staging tile, no synchronisation between epilogue warps.
+// ACT / RES / GAP / F32 / BF are compile-time for the configurations the embedding tower uses (-1 = read `ep`).
+template <int ACT, int RES, int GAP, int F32, int BF>
+__device__ __forceinline__ void epilogue_chunk(const GemmShape& sh, const GemmEpilogue& ep, const uint32_t (&r)[16],
+                                               int n0, int row, bool row_ok, int lane) {
   const int act = ACT >= 0 ? ACT : ep.act;
   const bool has_res = RES >= 0 ? (RES != 0) : (ep.residual != nullptr);
   const bool gap4 = GAP >= 0 ? (GAP != 0) : (ep.gap4 != 0);
-  const int n_base = c.n_t * sh.block_n + c0;
-  uint4 rr[2];
-  rr[0] = rr[1] = make_uint4(0u, 0u, 0u, 0u);
-  if (has_res && c.row_ok) {         // plain (coherent) loads: the residual may alias the output (in-place skip)
-    const uint16_t* rp = static_cast<const uint16_t*>(ep.residual) + (size_t)c.row * ep.ldr + n_base;
-    rr[0] = *reinterpret_cast<const uint4*>(rp);
-    if (n_base + 8 < sh.N) rr[1] = *reinterpret_cast<const uint4*>(rp + 8);
+  const bool out_f32 = F32 >= 0 ? (F32 != 0) : (ep.out_f32 != 0);
+  const int bf16 = BF >= 0 ? BF : ep.bf16;
+  const bool full = n0 + 16 <= sh.N;                 // N is a multiple of 8: a chunk holds 16 or 8 valid columns
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  if (ep.bias) {                                      // same addresses for the whole warp: broadcast L1 hits
+    const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q >= 2 && !full) break;
+      const float4 b = __ldg(bp + q);
+      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+    }
   }
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const int n0 = n_base + 8 * g;
-    if (n0 >= sh.N) break;                          // N is a multiple of 8
-    float v[8];
-    const float4 b0 = *reinterpret_cast<const float4*>(c.sb + c0 + 8 * g);
-    const float4 b1 = *reinterpret_cast<const float4*>(c.sb + c0 + 8 * g + 4);
-    v[0] = __uint_as_float(r[8 * g + 0]) + b0.x; v[1] = __uint_as_float(r[8 * g + 1]) + b0.y;
-    v[2] = __uint_as_float(r[8 * g + 2]) + b0.z; v[3] = __uint_as_float(r[8 * g + 3]) + b0.w;
-    v[4] = __uint_as_float(r[8 * g + 4]) + b1.x; v[5] = __uint_as_float(r[8 * g + 5]) + b1.y;
-    v[6] = __uint_as_float(r[8 * g + 6]) + b1.z; v[7] = __uint_as_float(r[8 * g + 7]) + b1.w;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act);
-    if (has_res && c.row_ok) {
-      const uint32_t w[4] = {rr[g].x, rr[g].y, rr[g].z, rr[g].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = ptx::unpack_h2(w[j], ep.bf16);
-        v[2 * j] += f.x;
-        v[2 * j + 1] += f.y;
-      }
-    }
-    int orow = c.row;                               // global output row
-    int srow = c.q * 32 + c.lane;                   // row inside the staged tile
-    bool store = c.row_ok;
-    if (gap4) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
-        v[j] += __shfl_xor_sync(0xffffffffu, v[j], 2);
-        v[j] *= 0.25f;
-      }
-      orow = c.row >> 2;
-      srow >>= 2;
-      store = c.row_ok && ((c.lane & 3) == 0);
-    }
-    if (ep.scale_target) {
-      // SE gating: v = gates of clip `row` for 8 channels; scale every pixel of that clip in place
-      if (c.row_ok) {
-        uint16_t* t = static_cast<uint16_t*>(ep.scale_target) + (size_t)c.row * ep.scale_npix * ep.ldo + n0;
-        for (int p = 0; p < ep.scale_npix; ++p, t += ep.ldo) {
-          const uint4 y4 = *reinterpret_cast<const uint4*>(t);
-          const uint32_t w[4] = {y4.x, y4.y, y4.z, y4.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = ptx::unpack_h2(w[j], ep.bf16);
-            o[j] = ptx::pack_h2(f.x * v[2 * j], f.y * v[2 * j + 1], ep.bf16);
-          }
-          *reinterpret_cast<uint4*>(t) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-      }
-    } else if (ep.out_f32) {
-      if (store) {
-        float* o = reinterpret_cast<float*>(ep.out) + (size_t)orow * ep.ldo + n0;
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-      }
+  for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], act);
+  // residual and 16-bit output rows are 32-byte aligned when the row pitch is a multiple of 16 elements
+  if (has_res && row_ok) {          // plain (coherent) loads: the residual may alias the output (in-place skip); each
+    uint32_t w[8];                  // thread reads exactly the bytes it overwrites below
+    const uint16_t* rp = static_cast<const uint16_t*>(ep.residual) + (size_t)row * ep.ldr + n0;
+    if (full && (ep.ldr & 15) == 0) {
+      ldg256(rp, w);
     } else {
-      uint4 pk;
-      pk.x = ptx::pack_h2(v[0], v[1], ep.bf16); pk.y = ptx::pack_h2(v[2], v[3], ep.bf16);
-      pk.z = ptx::pack_h2(v[4], v[5], ep.bf16); pk.w = ptx::pack_h2(v[6], v[7], ep.bf16);
-      if (c.staging) {
-        // SWIZZLE_128B staging tile: box = 64 columns; 16-byte piece index XORed with (row & 7)
-        const int col = c0 + 8 * g;
-        const int rows_box = gap4 ? kGemmBlockM / 4 : kGemmBlockM;
-        uint8_t* p = c.staging + (size_t)(col >> 6) * rows_box * 128 + (size_t)srow * 128 +
-                     ((((col & 63) >> 3) ^ (srow & 7)) << 4);
-        if (!gap4 || (c.lane & 3) == 0) *reinterpret_cast<uint4*>(p) = pk;   // rows past M are clipped by the TMA store
-      } else if (store) {
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out) + (size_t)orow * ep.ldo + n0) = pk;
-      }
+      const uint4 lo = *reinterpret_cast<const uint4*>(rp);
+      uint4 hi = make_uint4(0u, 0u, 0u, 0u);
+      if (full) hi = *reinterpret_cast<const uint4*>(rp + 8);
+      w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 f = ptx::unpack_h2(w[j], bf16);
+      v[2 * j] += f.x;
+      v[2 * j + 1] += f.y;
+    }
+  }
+  int orow = row;
+  bool store = row_ok;
+  if (gap4) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
+      v[j] += __shfl_xor_sync(0xffffffffu, v[j], 2);
+      v[j] *= 0.25f;
+    }
+    orow = row >> 2;
+    store = row_ok && ((lane & 3) == 0);
+  }
+  if (!store) return;
+  if (out_f32) {
+    float* o = reinterpret_cast<float*>(ep.out) + (size_t)orow * ep.ldo + n0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q >= 2 && !full) break;
+      *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  } else {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pk[j] = ptx::pack_h2(v[2 * j], v[2 * j + 1], bf16);
+    uint16_t* o = reinterpret_cast<uint16_t*>(ep.out) + (size_t)orow * ep.ldo + n0;
+    if (full && (ep.ldo & 15) == 0) {
+      stg256(o, pk);
+    } else {
+      *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (full) *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
   }
 }
 
-template <int kMinBlocks, int ACT, int RES, int GAP>
+template <int kMinBlocks, int ACT, int RES, int GAP, int F32, int BF>
 __global__ void __launch_bounds__(kGemmThreads, kMinBlocks)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_out, const GemmShape sh, const GemmEpilogue ep) {
+                    const GemmShape sh, const GemmEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int staging_rows = sh.tma_store ? (ep.gap4 ? kGemmBlockM / 4 : kGemmBlockM) : 0;
-  const SmemLayout L = smem_layout(sh.block_n, sh.block_k, sh.stages, staging_rows);
+  const SmemLayout L = smem_layout(sh.block_n, sh.block_k, sh.stages);
   const uint32_t a_bytes = (uint32_t)kGemmBlockM * sh.block_k * 2;
-  uint8_t* staging = sh.tma_store ? smem + L.staging_off : nullptr;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + kGemmMaxStages;
   uint64_t* tmem_full = empty_bar + kGemmMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_bias = reinterpret_cast<float*>(smem + L.bias_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int block_n = sh.block_n, stages = sh.stages;
@@ -171,7 +153,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmap_a);
     ptx::tma_prefetch_desc(&tmap_b);
-    if (sh.tma_store) ptx::tma_prefetch_desc(&tmap_out);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -244,35 +225,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: TMEM -> registers -> (smem staging -> TMA store | global) =====================
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    // The eight warps never synchronise with each other: each waits for the accumulator stage, converts its
+    // 16-column chunks (quarter q = its 32 TMEM lanes = 32 output rows; the two warps of a quarter take alternate
+    // chunks) and releases the stage.
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;                     // which of the two warps of this quarter (chunk parity)
-    const int et = (int)threadIdx.x - 64;                 // 0..255 among epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
-    int bias_buf = 0;
-    const bool bias_once = sh.n_tiles == 1;               // one column tile: the bias slice is the same for every tile
-    if (bias_once && et < block_n) s_bias[et] = (ep.bias && et < sh.N) ? __ldg(ep.bias + et) : 0.0f;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_t = tile / sh.n_tiles, n_t = tile - m_t * sh.n_tiles;
-      // per-tile slices alternate between two buffers: a warp that is already on tile i+1 writes the other buffer
-      // than the one laggards of tile i still read (the barrier below orders the reuse two tiles later)
-      float* sb = s_bias + bias_buf * 256;
-      if (!bias_once) {
-        if (et < block_n) {
-          const int n = n_t * block_n + et;
-          sb[et] = (ep.bias && n < sh.N) ? __ldg(ep.bias + n) : 0.0f;
-        }
-        bias_buf ^= 1;
-      }
-      if (staging && et == 0) ptx::tma_store_wait_read();  // previous tile's TMA stores have drained the staging tile
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // epilogue warps only
+      const int row = m_t * kGemmBlockM + q * 32 + lane;
+      const bool row_ok = row < sh.M;
+      const int n_tile0 = n_t * block_n;
+      const int n_lim = min(block_n, sh.N - n_tile0);     // valid columns of this tile
       ptx::mbar_wait(tmem_full + acc, acc_phase);
       ptx::tc_fence_after();
-      EpiCtx ctx{sh, ep, sb, staging, n_t, m_t * kGemmBlockM + q * 32 + lane, lane, q, false};
-      ctx.row_ok = ctx.row < sh.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * block_n);
-      const int n_lim = min(block_n, sh.N - n_t * block_n);  // valid columns of this tile
       // software-pipelined: the TMEM load of chunk i+1 is in flight while chunk i is processed
       uint32_t ra[16], rb[16];
       int c0 = half * 16;
@@ -282,32 +251,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ptx::tmem_ld_wait();
           const int c1 = c0 + 32;
           if (c1 < n_lim) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c1, rb);
-          epilogue_chunk<ACT, RES, GAP>(ctx, ra, c0);
+          epilogue_chunk<ACT, RES, GAP, F32, BF>(sh, ep, ra, n_tile0 + c0, row, row_ok, lane);
           if (c1 >= n_lim) break;
           ptx::tmem_ld_wait();
           c0 = c1 + 32;
           if (c0 < n_lim) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, ra);
-          epilogue_chunk<ACT, RES, GAP>(ctx, rb, c1);
+          epilogue_chunk<ACT, RES, GAP, F32, BF>(sh, ep, rb, n_tile0 + c1, row, row_ok, lane);
           if (c0 >= n_lim) break;
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tmem_empty + acc);   // TMEM stage may be overwritten by the next-but-one tile
-      if (staging) {
-        ptx::fence_proxy_async();                          // make this thread's smem writes visible to the TMA engine
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (et == 0) {
-          const int rows_box = ep.gap4 ? kGemmBlockM / 4 : kGemmBlockM;
-          const int n_boxes = (n_lim + 63) >> 6;
-          for (int j = 0; j < n_boxes; ++j)
-            ptx::tma_store_2d(&tmap_out, staging + (size_t)j * rows_box * 128, n_t * block_n + 64 * j, m_t * rows_box);
-          ptx::tma_store_commit();
-        }
-      }
       if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
     }
-    if (staging && et == 0) ptx::tma_store_wait_all();     // global writes complete before the kernel exits
   }
 
   ptx::tc_fence_before();
@@ -337,17 +294,15 @@ EncodeTiledFn get_encode_fn() {
 // Tile width by a small cost model: a CTA streams num_kb k-blocks of (16 KB A + bn*128 B W) per tile at roughly
 // 60 KB/us and spends ~0.01 us per output column in the epilogue; tiles are spread over the SMs in waves.
 // Few-tile problems (late layers, dense tower) get narrow tiles so all SMs work; big-M problems get the widest
-// tile with little column padding.  With several n-tiles the TMA-store boxes (64 columns) must not cross into
-// the neighbouring tile, so block_n is then a multiple of 64.
+// tile with little column padding.
 int pick_block_k(int K) { return K <= 16 ? 16 : (K <= 32 ? 32 : 64); }
 
-int pick_block_n(int N, int K, int m_tiles, int sm_count, bool tma_store) {
+int pick_block_n(int N, int K, int m_tiles, int sm_count) {
   const int num_kb = (K + kGemmBlockK - 1) / kGemmBlockK;
   int best = 16;
   double best_cost = 1e30;
   for (int bn = 16; bn <= 256; bn += 16) {
     const int n_tiles = (N + bn - 1) / bn;
-    if (tma_store && n_tiles > 1 && (bn & 63)) continue;
     const long long tiles = (long long)n_tiles * m_tiles;
     const long long waves = (tiles + sm_count - 1) / sm_count;
     const double load_us = num_kb * (16.0 + bn * 0.128) / 60.0;
@@ -401,59 +356,52 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   GemmShape sh;
   sh.M = M; sh.N = N; sh.K = K;
   sh.m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
-  // 16-bit outputs go through a swizzled smem tile and TMA stores (full 128-byte lines); fp32 outputs (the final
-  // embedding only) and non-dense outputs use direct stores.  Residual reads and the store of one tile touch
-  // exactly the same elements, so the in-place skip connection stays race-free.
-  sh.tma_store = (ep.out_f32 || ep.ldo != N || ep.scale_target) ? 0 : 1;
-  sh.block_n = block_n > 0 ? block_n : pick_block_n(N, K, sh.m_tiles, sm_count, sh.tma_store != 0);
+  // Every epilogue thread reads its residual bytes and then overwrites exactly those bytes, so the in-place skip
+  // connection (residual == out) is race-free.
+  sh.block_n = block_n > 0 ? block_n : pick_block_n(N, K, sh.m_tiles, sm_count);
   KWS_REQUIRE(sh.block_n % 16 == 0 && sh.block_n >= 16 && sh.block_n <= 256, "gemm: bad block_n %d", sh.block_n);
   sh.n_tiles = (N + sh.block_n - 1) / sh.block_n;
-  if (sh.tma_store && sh.n_tiles > 1 && (sh.block_n & 63)) sh.tma_store = 0;   // forced odd tile width: direct stores
-  const int staging_rows = sh.tma_store ? (ep.gap4 ? kGemmBlockM / 4 : kGemmBlockM) : 0;
   sh.block_k = pick_block_k(K);
   const int num_kb = (K + sh.block_k - 1) / sh.block_k;
   const int tiles_per_cta = (sh.m_tiles * sh.n_tiles + sm_count - 1) / sm_count;
   // Stage count = how many k-blocks (for single-k-block layers: how many TILES) may be in flight per CTA.  Memory-
   // bound small-K layers want as many as fit in ~half the SM's shared memory (so two CTAs co-reside).
   // Many-tile problems (the early layers: M = 10^5 rows, small K and N) are bound by the per-tile latency chain
-  // (TMEM load -> epilogue math -> staging -> TMA store), not by operand bandwidth: they run two CTAs per SM, each
+  // (TMEM load -> epilogue math -> store), not by operand bandwidth: they run two CTAs per SM, each
   // with half the shared memory and 256 TMEM columns (one accumulator stage when block_n > 128).
   const int tiles_total = sh.m_tiles * sh.n_tiles;
   const bool many_tiles = tiles_total >= 2 * sm_count;
   const size_t budget = ((num_kb <= 2 && sh.block_n <= 128) || (many_tiles && num_kb <= 4)) ? 110 * 1024 : 220 * 1024;
   sh.acc_stages = 2;
   int stages = kGemmMaxStages;
-  while (stages > 2 && smem_layout(sh.block_n, sh.block_k, stages, staging_rows).total + 1024 > budget) --stages;
+  while (stages > 2 && smem_layout(sh.block_n, sh.block_k, stages).total + 1024 > budget) --stages;
   const int useful = num_kb * (tiles_per_cta < 8 ? tiles_per_cta : 8) + 1;
   if (stages > useful) stages = useful;
   if (stages < 2) stages = 2;
   sh.stages = stages;
-  const size_t smem = smem_layout(sh.block_n, sh.block_k, sh.stages, staging_rows).total + 1024;
+  const size_t smem = smem_layout(sh.block_n, sh.block_k, sh.stages).total + 1024;
   KWS_REQUIRE(smem <= 227 * 1024, "gemm: tile configuration does not fit shared memory");
 
-  CUtensorMap ta, tb, tout;
+  CUtensorMap ta, tb;
   int rc = make_tmap_h16(&ta, a, (uint64_t)M, (uint64_t)K, kGemmBlockM, ep.bf16, (uint32_t)sh.block_k);
   if (rc != KWS_OK) return rc;
   rc = make_tmap_h16(&tb, w, (uint64_t)N, (uint64_t)K, (uint32_t)sh.block_n, ep.bf16, (uint32_t)sh.block_k);
   if (rc != KWS_OK) return rc;
-  if (sh.tma_store) {
-    rc = make_tmap_h16(&tout, ep.out, (uint64_t)(ep.gap4 ? M / 4 : M), (uint64_t)N, (uint32_t)staging_rows, ep.bf16);
-    if (rc != KWS_OK) return rc;
-  } else {
-    tout = ta;   // unused
-  }
   const int tiles = sh.m_tiles * sh.n_tiles;
   // Memory/latency-bound shapes (small K, many tiles): two co-resident CTAs per SM hide each other's TMA, TMEM and
   // store latencies.  Needs half the shared memory and at most 256 TMEM columns per CTA.
   const bool two = smem <= 112 * 1024 && tiles >= 2 * sm_count;
   if (two && sh.block_n > 128) sh.acc_stages = 1;
-  // compile-time specialised epilogues for the (activation, residual, gap) combinations of the tower; anything else
-  // runs the fully run-time variant
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmShape, const GemmEpilogue);
-  KernelFn k1 = gemm_tcgen05_kernel<1, -1, -1, -1>, k2 = gemm_tcgen05_kernel<2, -1, -1, -1>;
+  // compile-time specialised epilogues for the (activation, residual, gap) combinations of the tower in its default
+  // fp16 / 16-bit-output form; anything else (bf16 storage, fp32 output, selu) runs the fully run-time variant
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const GemmShape, const GemmEpilogue);
+  KernelFn k1 = gemm_tcgen05_kernel<1, -1, -1, -1, -1, -1>, k2 = gemm_tcgen05_kernel<2, -1, -1, -1, -1, -1>;
   const int res = ep.residual ? 1 : 0;
-#define KWS_GEMM_VARIANT(A, R, G) \
-  if (ep.act == A && res == R && ep.gap4 == G) { k1 = gemm_tcgen05_kernel<1, A, R, G>; k2 = gemm_tcgen05_kernel<2, A, R, G>; }
+#define KWS_GEMM_VARIANT(A, R, G)                                                \
+  if (ep.act == A && res == R && ep.gap4 == G && !ep.out_f32 && !ep.bf16) {      \
+    k1 = gemm_tcgen05_kernel<1, A, R, G, 0, 0>;                                  \
+    k2 = gemm_tcgen05_kernel<2, A, R, G, 0, 0>;                                  \
+  }
   KWS_GEMM_VARIANT(kActSwish, 0, 0)
   KWS_GEMM_VARIANT(kActNone, 0, 0)
   KWS_GEMM_VARIANT(kActNone, 1, 0)
@@ -465,7 +413,7 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   KWS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = two ? 2 : 1;
   const int grid = tiles < per_sm * sm_count ? tiles : per_sm * sm_count;
-  KWS_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, stream, ta, tb, tout, sh, ep));
+  KWS_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, stream, ta, tb, sh, ep));
   return KWS_OK;
 }
 

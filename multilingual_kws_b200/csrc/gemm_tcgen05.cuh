@@ -6,12 +6,13 @@
 //
 //   D[M,N] = epilogue( A[M,K] (fp16|bf16, K-major) x W[N,K]^T (same type, K-major) )      fp32 accumulate in TMEM
 //   epilogue: + bias[N] (folded BatchNorm), activation, + residual[M,N], optional 4-row mean (GAP of the
-//   2x2 top activation); 16-bit outputs are staged in a SWIZZLE_128B smem tile and written with TMA stores
-//   (full 128-byte lines, clipped at the tensor bounds), fp32 outputs with direct 16-byte stores.
+//   2x2 top activation).  An epilogue thread owns one accumulator row and 16 consecutive columns at a time = 32
+//   contiguous output bytes, written (and, for the skip connection, read) with one 256-bit access: full sectors,
+//   no staging tile and no synchronisation between the epilogue warps.
 //
 // Roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane)
 // + TMEM allocation, warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter split the
-// 16-column chunks; the tile's bias slice is staged in smem once per tile).  Pipelines: smem ring
+// 16-column chunks; the bias is read through L1 as warp-uniform 16-byte loads).  Pipelines: smem ring
 // full/empty mbarriers (TMA <-> MMA), 2 TMEM accumulator stages full/empty (MMA <-> epilogue), so the
 // epilogue of tile i overlaps the loads + MMAs of tile i+1.  Tiles: 128 x BLOCK_N x 64, SWIZZLE_128B.
 #pragma once
@@ -37,10 +38,6 @@ struct GemmEpilogue {
   int out_f32;                       // 1: store float
   int gap4;                          // 1: average each aligned group of 4 rows -> row m/4
   int bf16;                          // storage/operand type of A, W, residual, 16-bit out: 1 bf16, 0 fp16
-  // SE gating mode: instead of storing the result (the sigmoid gates g[m, n], one row per clip), multiply the
-  // activation tensor scale_target[m, p, n] (p < scale_npix, row pitch ldo) by it in place.
-  void* scale_target;
-  int scale_npix;
 };
 
 struct GemmShape {
@@ -50,7 +47,6 @@ struct GemmShape {
   int block_k;                       // 16 / 32 / 64 elements per k-block = SWIZZLE_32B / 64B / 128B tiles: small-K layers
                                      // get narrow tiles, so many more of them fit in flight (memory-level parallelism)
   int m_tiles, n_tiles;
-  int tma_store;                     // 1: epilogue stages the tile in swizzled smem and writes it with TMA stores
   int acc_stages;                    // TMEM accumulator stages per CTA: 2, or 1 for wide tiles (block_n > 128) that
                                      // should still leave room for a second CTA on the SM (256 of the 512 columns)
 };
