@@ -196,9 +196,49 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
     value = world * B / (ms_step * 1e-3)
 
+    # ---- the same device-resident work with consecutive steps on alternating streams (what the host pipeline does):
+    # late layers are latency-bound and leave SMs idle, early layers are throughput-bound, neighbouring steps fill
+    # each other's gaps.  Region timing: first launch -> last kernel, L2 flushes included, / K.
+    n_str = 3
+    ov_streams = [torch.cuda.Stream(device=dev) for _ in range(n_str)]
+    ov_bufs = [(torch.empty_like(feats), torch.empty_like(emb),
+                torch.empty(emb_model.workspace_bytes(B), dtype=torch.uint8, device=dev)) for _ in range(n_str)]
+
+    def ov_step(k):
+        f, o, w_ = ov_bufs[k % n_str]
+        st = ov_streams[k % n_str]
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            fe.forward(pcm, out=f)
+            emb_model.forward_device(f, out=o, workspace=w_)
+
+    def ov_join():
+        for st in ov_streams:
+            torch.cuda.current_stream().wait_stream(st)
+
+    ms_overlap = None
+    if not args.no_graph:
+        for k in range(max(args.warmup, 3) * n_str):
+            ov_step(k)
+        ov_join()
+        barrier()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        for k in range(args.steps):
+            flush.zero_()
+            ov_step(k)
+        ov_join()
+        e_ev.record()
+        barrier()
+        ms_overlap = s_ev.elapsed_time(e_ev) / args.steps
+        if world > 1:
+            t = torch.tensor([ms_overlap], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_overlap = float(t.item())
+
     # ---- e2e: public API, host buffers (pinned), H2D + D2H inside the timed region
     from multilingual_kws_b200.pipeline import EmbedPipeline
-    pipe = EmbedPipeline(fe, emb_model, n_samples=16000, sub_batch=B, depth=3)
+    pipe = EmbedPipeline(fe, emb_model, n_samples=16000, sub_batch=B, depth=6, streams=3)
     # host buffers: two input sets in write-combined pinned memory (kws_host_alloc), two pinned result buffers
     pcm_pinned2 = [pipe.alloc_input(B), pipe.alloc_input(B)]
     pcm_pinned2[0].copy_(torch.from_numpy(pcm_host))
@@ -339,6 +379,10 @@ def run_ours(args, rank, local_rank, world):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype + " storage / tensor-core operands, fp32 accumulate; frontend int16/int32/uint64 fixed point",
             "data": "synthetic",
+            "value_note": "value / ms_per_step: one step at a time on one stream (CUDA events around each step, L2 flushed "
+                          "before it); overlapped: K steps rotating over 3 streams, whole region / K, flushes included",
+            "overlapped": None if ms_overlap is None else {"value": world * B / (ms_overlap * 1e-3), "unit": UNIT,
+                                                           "ms_per_step": ms_overlap, "streams": n_str},
             "config": {"workload": f"configs[1]: log-mel frontend + EfficientNet-B0 embedding forward, batch {B} x 1 s @ 16 kHz clips per GPU",
                        "global_batch": B * world, "clip_samples": 16000, "parallelism": f"dp{world} (clips sharded, no collective)",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)", "chunk": args.chunk, "chunk_late": args.chunk_late,
@@ -346,7 +390,7 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 32000, "d2h_bytes_per_step": B * emb_model.output_dim * 4,
                     "ms_per_step": ms_e2e,
                     "timing": "whole K-step region (first enqueue -> last download, L2 flushes included) / K; run_host "
-                              "enqueues only, so upload i+1 / kernels i / download i-1 overlap (3 device slots)",
+                              "enqueues only: upload i+1 / kernels i / download i-1 overlap, and consecutive steps rotate over three compute streams (6 device slots)",
                     "ms_per_blocking_call_wall": ms_e2e_sync,
                     "host_buffers": "PCM in write-combined pinned memory (kws_host_alloc), results in pinned memory"},
             "gpu_launches": launches_per_step * args.steps,

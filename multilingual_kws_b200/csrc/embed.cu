@@ -611,7 +611,7 @@ static int embed_forward_impl(kws_embed_t* m, const float* d_feats, int batch, f
     const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
     cudaGraphDestroy(graph);
     KWS_CUDA_CHECK(ie);
-    if (m->graphs.size() >= 8) {
+    if (m->graphs.size() >= 32) {
       cudaGraphExecDestroy(m->graphs.front().exec);
       m->graphs.erase(m->graphs.begin());
     }

@@ -149,9 +149,15 @@ class EmbeddingModel:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def forward_device(self, feats: torch.Tensor, out: Optional[torch.Tensor] = None, tap_op: int = -1):
+    def workspace_bytes(self, batch: int) -> int:
+        return int(_lib.lib().kws_embed_workspace_bytes(self._h, int(batch)))
+
+    def forward_device(self, feats: torch.Tensor, out: Optional[torch.Tensor] = None, tap_op: int = -1,
+                       workspace: Optional[torch.Tensor] = None):
         """feats: CUDA float32 [B,49,40] (contiguous) -> CUDA float32 [B, output_dim].  With tap_op >= 0 also
-        returns that op's output (bf16 [B, elems], fp32 for the last op)."""
+        returns that op's output (bf16 [B, elems], fp32 for the last op).  `workspace` (uint8 CUDA tensor of at least
+        workspace_bytes(B)) replaces the model's own scratch: forwards that run concurrently on different streams
+        must not share one."""
         if feats.dim() == 4 and feats.shape[-1] == 1:
             feats = feats[..., 0]
         if feats.dim() != 3 or tuple(feats.shape[1:]) != self.input_hw:
@@ -160,7 +166,9 @@ class EmbeddingModel:
         B = feats.shape[0]
         if out is None:
             out = torch.empty((B, self.output_dim), dtype=torch.float32, device=self.device)
-        ws = self._workspace(B)
+        ws = self._workspace(B) if workspace is None else workspace
+        if ws.numel() < self.workspace_bytes(B):
+            raise ValueError("workspace too small")
         tap = None
         tap_ptr = None
         if tap_op >= 0:

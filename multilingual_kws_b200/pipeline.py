@@ -3,18 +3,22 @@
 Work is cut into jobs of at most `sub_batch` clips.  Every job is three stream-ordered pieces:
 
     H2D  (upload stream)    pinned PCM        -> device slot s
-    run  (caller's stream)  frontend kernel + embedding graph on slot s
+    run  (compute stream)   frontend kernel + embedding graph on slot s
     D2H  (download stream)  device embeddings -> pinned result rows
 
-with `depth` device slots cycled round-robin.  The two copy directions have their own streams (and their own copy
+with `depth` device slots cycled round-robin and `streams` compute streams taken in turn.  Consecutive jobs therefore
+overlap on the device as well: the late layers of the network work on small feature maps and are latency-bound
+(they leave most SMs idle), the early layers are throughput-bound, and the two phases of neighbouring jobs fill
+each other's gaps.  Every slot has its own embedding workspace.  The two copy directions have their own streams (and their own copy
 engines on the device), so the upload of job k+1 and the download of job k-1 overlap the kernels of job k, across
 sub-batches of one call and across consecutive calls: `run_host()` only enqueues.  The embedding's CUDA graphs are
 keyed by (device buffers, batch), so cycling a fixed set of slots replays them instead of re-capturing.
 
 Slot reuse is ordered by events only (no host synchronisation inside `run_host`):
     upload(k)  waits  ran(k - depth)        the PCM slot has been consumed by the frontend
-    run(k)     waits  uploaded(k), downloaded(k - depth)
+    run(k)     waits  uploaded(k), downloaded(k - depth), and whatever preceded run_host on the caller's stream
     download(k) waits ran(k)
+(depth is a multiple of streams, so job k and job k - depth also share a compute stream.)
 """
 from __future__ import annotations
 
@@ -29,11 +33,13 @@ from .model import EmbeddingModel
 
 class EmbedPipeline:
     def __init__(self, frontend: MicroFrontend, model: EmbeddingModel, n_samples: int = 16000, sub_batch: int = 512,
-                 depth: int = 3):
-        if depth < 2:
-            raise ValueError("EmbedPipeline needs at least two device slots")
+                 depth: int = 4, streams: int = 2):
+        if depth < 2 or streams < 1 or depth % streams:
+            raise ValueError("EmbedPipeline needs at least two device slots, depth a multiple of streams")
         self.fe, self.model, self.n, self.sub, self.depth = frontend, model, int(n_samples), int(sub_batch), int(depth)
         dev = model.device
+        self._compute = [torch.cuda.Stream(device=dev) for _ in range(int(streams))]
+        self._ws = [torch.empty(model.workspace_bytes(self.sub), dtype=torch.uint8, device=dev) for _ in range(depth)]
         frames = frontend.num_frames(self.n)
         self._pcm = [torch.empty((self.sub, self.n), dtype=torch.int16, device=dev) for _ in range(depth)]
         self._feat = [torch.empty((self.sub, frames, frontend.num_channels), dtype=torch.float32, device=dev)
@@ -67,10 +73,12 @@ class EmbedPipeline:
         B = pcm_host.shape[0]
         if out_host is None:
             out_host = self.alloc_output(B)
-        compute = torch.cuda.current_stream()
+        caller = torch.cuda.current_stream()
         for b0 in range(0, B, self.sub):
             nb = min(self.sub, B - b0)
             k, s = self._jobs, self._jobs % self.depth
+            compute = self._compute[k % len(self._compute)]
+            compute.wait_stream(caller)
             with torch.cuda.stream(self._up):
                 if k >= self.depth:
                     self._up.wait_event(self._ran[s])
@@ -79,9 +87,10 @@ class EmbedPipeline:
             compute.wait_event(self._uploaded[s])
             if k >= self.depth:
                 compute.wait_event(self._downloaded[s])
-            self.fe.forward(self._pcm[s][:nb], out_scale=FEATURE_SCALE, out=self._feat[s][:nb])
-            self.model.forward_device(self._feat[s][:nb], out=self._emb[s][:nb])
-            self._ran[s].record(compute)
+            with torch.cuda.stream(compute):
+                self.fe.forward(self._pcm[s][:nb], out_scale=FEATURE_SCALE, out=self._feat[s][:nb])
+                self.model.forward_device(self._feat[s][:nb], out=self._emb[s][:nb], workspace=self._ws[s])
+                self._ran[s].record(compute)
             with torch.cuda.stream(self._down):
                 self._down.wait_event(self._ran[s])
                 out_host[b0:b0 + nb].copy_(self._emb[s][:nb], non_blocking=True)
@@ -95,8 +104,12 @@ class EmbedPipeline:
         cur = torch.cuda.current_stream()
         cur.wait_stream(self._down)
         cur.wait_stream(self._up)
+        for c in self._compute:
+            cur.wait_stream(c)
 
     def synchronize(self) -> None:
         """Block the host until every enqueued job has delivered its rows."""
+        for c in self._compute:
+            c.synchronize()
         self._down.synchronize()
         self._up.synchronize()

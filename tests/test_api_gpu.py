@@ -192,9 +192,9 @@ def test_host_pipeline_back_to_back_calls(world):
     inputs = [torch.roll(pcm, shifts=i, dims=0).contiguous() for i in range(7)]
     want = [model.forward_device(fe.forward(x.cuda())).cpu() for x in inputs]
     pinned = [x.pin_memory() for x in inputs]
-    for sub, depth in ((n, 2), (n, 3), (max(1, n // 3), 3)):
-        pipe = EmbedPipeline(fe, model, n_samples=16000, sub_batch=sub, depth=depth)
-        if depth == 3:                                          # write-combined upload buffers from the C ABI
+    for sub, depth, streams in ((n, 2, 1), (n, 4, 2), (max(1, n // 3), 3, 3)):
+        pipe = EmbedPipeline(fe, model, n_samples=16000, sub_batch=sub, depth=depth, streams=streams)
+        if depth >= 3:                                          # write-combined upload buffers from the C ABI
             pinned = [pipe.alloc_input(n) for _ in inputs]
             for dst, src in zip(pinned, inputs):
                 dst.copy_(src)
