@@ -96,6 +96,7 @@ constexpr int kDwThreads = 256;
 struct DwSmem {
   uint32_t in_bytes, out_off, pooled_off, part_off, s_off, red_off, bar_off, w_off, w_floats, total;
   uint32_t in2_off;   // second input buffer (0: single-buffered)
+  uint32_t zero_off;  // one all-zero input row (the padded rows of the early-layer specialisations read it)
   int PL;   // pixel lanes per channel pair
 };
 constexpr uint32_t kDwSmemCap = 227 * 1024;
@@ -116,6 +117,11 @@ __host__ __device__ inline DwSmem dw_smem(const DwseParams& P, int G) {
   L.w_off = (L.bar_off + 16 + 15) & ~15u;
   if (L.w_floats * 4 > 40 * 1024) L.w_floats = 0;
   L.total = L.w_off + L.w_floats * 4;
+  L.zero_off = 0;
+  if ((uint32_t)P.W * (P.C >> 1) * 4 <= 4096) {
+    L.zero_off = (L.total + 15) & ~15u;
+    L.total = L.zero_off + 4096;
+  }
   // A layer whose group does not leave room for a second CTA on the SM (block2a: 96 KB of input per clip) would
   // expose the whole bulk-load latency of every group; if two input buffers fit, the next group's load is issued
   // while the current one is convolved.
@@ -168,9 +174,9 @@ __device__ __forceinline__ void dw_small_item(const uint32_t* __restrict__ in_g,
 
 // Early-stage maps (25x20 ... 7x5): one output ROW per call with every column bound, smem offset and window slot a
 // compile-time constant (geometry, stride, padding and channel count are template parameters), so the row costs
-// K*S shared loads + K*K*2 FMAs per output pixel and no branches; padded rows are handled by zero-selects.
+// K*S shared loads + K*K*2 FMAs per output pixel and no branches; rows in the padding read an all-zero smem row.
 template <int K, int S, int W, int WO, int PLFT, int C2>
-__device__ __forceinline__ void dw_strip_row(const uint32_t* const (&rowp)[K], const bool (&row_ok)[K],
+__device__ __forceinline__ void dw_strip_row(const uint32_t* const (&rowp)[K],
                                              const float2 (&wreg)[K * K], float2 bias, int bf16,
                                              uint32_t* __restrict__ orow, float& sum0, float& sum1) {
   float2 win[K][K];
@@ -184,12 +190,8 @@ __device__ __forceinline__ void dw_strip_row(const uint32_t* const (&rowp)[K], c
 #pragma unroll
         for (int kh = 0; kh < K; ++kh) {
           float2 v = make_float2(0.0f, 0.0f);
-          if (c >= 0 && c < W) {                         // compile-time
-            const float2 t = ptx::unpack_h2(rowp[kh][c * C2], bf16);
-            v.x = row_ok[kh] ? t.x : 0.0f;
-            v.y = row_ok[kh] ? t.y : 0.0f;
-          }
-          win[kh][slot] = v;
+          if (c >= 0 && c < W) v = ptx::unpack_h2(rowp[kh][c * C2], bf16);   // compile-time bound; padded rows
+          win[kh][slot] = v;                                                  // point at the all-zero row
         }
       }
     }
@@ -212,8 +214,40 @@ __device__ __forceinline__ void dw_strip_row(const uint32_t* const (&rowp)[K], c
 
 // GEOM: 0 = generic (runtime geometry, row strips); 1..6 = the tiny-map geometries of EfficientNet-B0 at 49x40 input
 // (whole image in registers); 7..11 = its early-stage geometries (compile-time row strips).
+// Squeeze-excite of the narrow layers (C <= 256: every block up to 3b), all clips of a group, written to need only
+// a handful of registers (it shares the kernel with the convolution's weight / window registers).
+// FC1: eight lanes per (clip, squeeze unit) pair, each summing every eighth channel, then a 3-step butterfly: the
+// order of the additions depends only on the clip, never on how clips are grouped.
+// FC2: thread = channel; gate[g][c] = sigmoid(b2[c] + s[g] . w2[:][c]) overwrites the pooled sums.
+__device__ __forceinline__ void se_narrow(float* s_pool, float* s_se, const float* w_se1, const float* b_se1,
+                                          const float* w_se2, const float* b_se2, int C, int se, int gn, float inv_npix) {
+  const int tid = threadIdx.x, sub = tid & 7;
+  for (int pair = tid >> 3; pair < ((gn * se + 3) & ~3); pair += kDwThreads / 8) {   // whole warps stay in the loop
+    const bool ok = pair < gn * se;
+    const int g = ok ? pair / se : 0, j = ok ? pair - g * se : 0;
+    const float* pp = s_pool + g * C;
+    const float* wp = w_se1 + j * C;
+    float acc = 0.0f;
+    for (int c = sub; c < C; c += 8) acc = fmaf(pp[c], wp[c], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (ok && sub == 0) s_se[pair] = swish(acc * inv_npix + b_se1[j]);
+  }
+  __syncthreads();
+  if (tid < C) {
+    const float b2 = b_se2[tid];
+    for (int g = 0; g < gn; ++g) {
+      float a = b2;
+      for (int j = 0; j < se; ++j) a = fmaf(w_se2[j * C + tid], s_se[g * se + j], a);
+      s_pool[g * C + tid] = sigmoidf(a);
+    }
+  }
+  __syncthreads();
+}
+
 template <int K, int S, int GEOM>
-__global__ void __launch_bounds__(kDwThreads)
+__global__ void __launch_bounds__(kDwThreads, 2)     // <= 128 registers: two CTAs per SM wherever shared memory allows
 dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint16_t* __restrict__ y) {
   extern __shared__ __align__(128) uint8_t smem[];
   const DwSmem L = dw_smem(P, G);
@@ -225,6 +259,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
   float* s_se = reinterpret_cast<float*>(smem + L.s_off);                     // [G][se]
   float* s_red = reinterpret_cast<float*>(smem + L.red_off);                  // [se][warps][4]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  const uint32_t* s_zero = reinterpret_cast<const uint32_t*>(smem + L.zero_off);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = P.C, C2 = C >> 1, npix = P.Ho * P.Wo;
@@ -253,6 +288,8 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
     ptx::mbar_init(bar + 1, 1);
     ptx::fence_barrier_init();
   }
+  if (L.zero_off)
+    for (int i = tid; i < 1024; i += kDwThreads) reinterpret_cast<uint32_t*>(smem + L.zero_off)[i] = 0u;
   __syncthreads();
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();              // weights / barrier set-up above overlapped the predecessor's tail
@@ -321,6 +358,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
               const int r = ho * S + kh - P.pad_top;
               row_ok[kh] = (r >= 0) && (r < P.H);
               rowp[kh] = in_g + (size_t)(row_ok[kh] ? r : 0) * P.W * C2;
+              if (GEOM >= 7 && !row_ok[kh]) rowp[kh] = s_zero + cp;
             }
             uint32_t* orow = s_out + ((size_t)g * npix + (size_t)ho * P.Wo) * C2 + cp;
             if constexpr (GEOM >= 7) {
@@ -330,7 +368,7 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
               constexpr int GWO = GEOM == 7 ? 20 : (GEOM <= 9 ? 10 : 5);
               constexpr int GPL = (GEOM == 8) ? 0 : ((GEOM == 11) ? 2 : 1);
               constexpr int GC2 = GEOM == 7 ? 16 : (GEOM == 8 ? 48 : (GEOM <= 10 ? 72 : 120));
-              dw_strip_row<K, S, GW, GWO, GPL, GC2>(rowp, row_ok, wreg, bias, P.bf16, orow, sum0, sum1);
+              dw_strip_row<K, S, GW, GWO, GPL, GC2>(rowp, wreg, bias, P.bf16, orow, sum0, sum1);
             } else {
             float2 win[K][K];
             for (int wo_base = 0; wo_base < P.Wo; wo_base += K) {
@@ -408,6 +446,10 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
       continue;
     }
 
+    const bool narrow = C <= kDwThreads;
+    if (narrow) {
+      se_narrow(s_pool, s_se, w_se1, b_se1, w_se2, b_se2, C, P.se, gn, inv_npix);
+    } else {
     // ---- SE reduce: s[g][j] = swish(b1[j] + mean_g . w1[j][:]).  Every thread owns channels c = tid + 256 i and
     // streams its slice of every weight row (coalesced, independent loads -> deep memory-level parallelism);
     // partial dot products are reduced by warp shuffles, then across the 8 warps through smem.
@@ -478,29 +520,30 @@ dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint
     }
     __syncthreads();
 
-    // ---- scale and store: 16-byte vectors (8 channels), coalesced; no div/mod in the loop
+    }   // wide in-kernel SE
+
+    // ---- scale and store: 16-byte vectors (8 channels).  A thread keeps one channel vector (its 8 gates stay in
+    // registers for the clip) and walks the pixels; consecutive threads write consecutive 16-byte pieces.
     {
       const int C8 = C >> 3;                                  // uint4 vectors per pixel
-      const int vec_per_clip = npix * C8;
-      const int step = kDwThreads % C8;
-      for (int g = 0; g < gn; ++g) {
-        const uint4* src = reinterpret_cast<const uint4*>(s_out) + (size_t)g * vec_per_clip;
-        uint4* dst = reinterpret_cast<uint4*>(y) + ((size_t)(g0 + g) * vec_per_clip);
-        const float* gate = s_pool + g * C;
-        int c8 = tid % C8;
-        for (int i = tid; i < vec_per_clip; i += kDwThreads) {
-          const uint4 v = src[i];
-          const float4 g0v = *reinterpret_cast<const float4*>(gate + 8 * c8);
-          const float4 g1v = *reinterpret_cast<const float4*>(gate + 8 * c8 + 4);
-          float2 x;
-          uint4 o;
-          x = ptx::unpack_h2(v.x, P.bf16); o.x = ptx::pack_h2(x.x * g0v.x, x.y * g0v.y, P.bf16);
-          x = ptx::unpack_h2(v.y, P.bf16); o.y = ptx::pack_h2(x.x * g0v.z, x.y * g0v.w, P.bf16);
-          x = ptx::unpack_h2(v.z, P.bf16); o.z = ptx::pack_h2(x.x * g1v.x, x.y * g1v.y, P.bf16);
-          x = ptx::unpack_h2(v.w, P.bf16); o.w = ptx::pack_h2(x.x * g1v.z, x.y * g1v.w, P.bf16);
-          dst[i] = o;
-          c8 += step;
-          if (c8 >= C8) c8 -= C8;
+      const int PLg = kDwThreads / C8;                        // pixel lanes (C <= 1152 -> C8 <= 144 -> PLg >= 1)
+      const int c8 = tid % C8, pl8 = tid / C8;
+      if (pl8 < PLg) {
+        for (int g = 0; g < gn; ++g) {
+          const uint4* src = reinterpret_cast<const uint4*>(s_out) + (size_t)g * npix * C8 + c8;
+          uint4* dst = reinterpret_cast<uint4*>(y) + ((size_t)(g0 + g) * npix * C8) + c8;
+          const float4 g0v = *reinterpret_cast<const float4*>(s_pool + g * C + 8 * c8);
+          const float4 g1v = *reinterpret_cast<const float4*>(s_pool + g * C + 8 * c8 + 4);
+          for (int px = pl8; px < npix; px += PLg) {
+            const uint4 v = src[(size_t)px * C8];
+            float2 x;
+            uint4 o;
+            x = ptx::unpack_h2(v.x, P.bf16); o.x = ptx::pack_h2(x.x * g0v.x, x.y * g0v.y, P.bf16);
+            x = ptx::unpack_h2(v.y, P.bf16); o.y = ptx::pack_h2(x.x * g0v.z, x.y * g0v.w, P.bf16);
+            x = ptx::unpack_h2(v.z, P.bf16); o.z = ptx::pack_h2(x.x * g1v.x, x.y * g1v.y, P.bf16);
+            x = ptx::unpack_h2(v.w, P.bf16); o.w = ptx::pack_h2(x.x * g1v.z, x.y * g1v.w, P.bf16);
+            dst[(size_t)px * C8] = o;
+          }
         }
       }
     }
