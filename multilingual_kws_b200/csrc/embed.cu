@@ -343,7 +343,7 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
         P.b_se2 = B.vec(std::vector<float>(b2->data, b2->data + cexp));
         CK(P.w_dw && P.b_dw && P.w_se1 && P.b_se1 && P.w_se2 && P.b_se2);
         P.se_external = 0; P.pooled_out = nullptr;
-        if (cexp >= 240 && m->se_via_gemm) {
+        if (cexp > 256 && m->se_via_gemm) {     // C <= 256 runs the in-kernel (narrow) squeeze-excite
           // wide layer: SE as two batched tensor-core GEMMs.  FC1: [B,C] x W1[se_pad,C]^T (+b1, swish);
           // FC2: [B,se_pad] x W2[C,se_pad]^T (+b2, sigmoid).  Padding rows / columns are zero.
           const int sp = (se + 15) & ~15;
