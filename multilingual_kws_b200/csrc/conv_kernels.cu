@@ -36,12 +36,14 @@ constexpr int kStemC = 32;
 __global__ void __launch_bounds__(kStemThreads)
 stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, uint16_t* __restrict__ out) {
   extern __shared__ __align__(128) uint8_t smem[];
-  float* s_in = reinterpret_cast<float*>(smem);                     // [H*W]
-  float* s_w = s_in + ((P.H * P.W + 3) & ~3);                        // [9][32]
+  float* s_in = reinterpret_cast<float*>(smem);                     // [(H+2)*(W+2)]: the clip inside a ring of zeros
+  const int HP = P.H + 2, WP = P.W + 2;
+  float* s_w = s_in + ((HP * WP + 3) & ~3);                          // [9][32]
   float* s_b = s_w + 9 * kStemC;                                     // [32]
   const int tid = threadIdx.x;
   for (int i = tid; i < 9 * kStemC; i += kStemThreads) s_w[i] = P.w[i];
   if (tid < kStemC) s_b[tid] = P.bias[tid];
+  for (int i = tid; i < HP * WP; i += kStemThreads) s_in[i] = 0.0f;  // ZeroPadding2D pads the NORMALISED input with 0
   const int npix = P.Ho * P.Wo;
   __syncthreads();
   // item = (pixel, group of 8 output channels); 256 % 4 == 0, so a thread's channel group never changes and its
@@ -54,38 +56,42 @@ stem_conv_kernel(const float* __restrict__ feats, int batch, StemParams P, uint1
     for (int j = 0; j < 8; ++j) wr[t][j] = s_w[t * kStemC + g * 8 + j];
 #pragma unroll
   for (int j = 0; j < 8; ++j) br[j] = s_b[g * 8 + j];
+  // a thread's pixels are p0, p0 + 64, ...: (ho, wo) advance by (64 / Wo, 64 % Wo) with a carry, no division in the loop
+  const int p0 = tid >> 2, dq = (kStemThreads / 4) / P.Wo, dr = (kStemThreads / 4) % P.Wo;
+  const int ho0 = p0 / P.Wo, wo0 = p0 - ho0 * P.Wo;
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   for (int clip = blockIdx.x; clip < batch; clip += gridDim.x) {
     __syncthreads();
     const float* src = feats + (size_t)clip * P.H * P.W;
-    for (int i = tid; i < P.H * P.W; i += kStemThreads) s_in[i] = fmaf(__ldg(src + i), P.in_scale, P.in_shift);
+    for (int i = tid; i < P.H * P.W; i += kStemThreads) {
+      const int r = i / P.W, c = i - r * P.W;
+      s_in[(r + 1) * WP + c + 1] = fmaf(__ldg(src + i), P.in_scale, P.in_shift);
+    }
     __syncthreads();
-    for (int item = tid; item < npix * 4; item += kStemThreads) {
-      const int p = item >> 2;
-      const int ho = p / P.Wo, wo = p - ho * P.Wo;
+    int ho = ho0, wo = wo0;
+    for (int p = p0; p < npix; p += kStemThreads / 4) {
+      // taps (kh, kw) read input (2 ho + kh - pad_top, 2 wo + kw - pad_left); +1 for the ring: always inside the buffer
+      const float* xin = s_in + (ho * 2 - P.pad_top + 1) * WP + (wo * 2 - P.pad_left + 1);
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = br[j];
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int r = ho * 2 + kh - P.pad_top;
-        if (r < 0 || r >= P.H) continue;
+      for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const int c = wo * 2 + kw - P.pad_left;
-          if (c < 0 || c >= P.W) continue;
-          const float x = s_in[r * P.W + c];
+          const float x = xin[kh * WP + kw];
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, wr[kh * 3 + kw][j], acc[j]);
         }
-      }
       uint4 pk;
       pk.x = ptx::pack_h2(swish(acc[0]), swish(acc[1]), P.bf16);
       pk.y = ptx::pack_h2(swish(acc[2]), swish(acc[3]), P.bf16);
       pk.z = ptx::pack_h2(swish(acc[4]), swish(acc[5]), P.bf16);
       pk.w = ptx::pack_h2(swish(acc[6]), swish(acc[7]), P.bf16);
       *reinterpret_cast<uint4*>(out + ((size_t)clip * npix + p) * kStemC + g * 8) = pk;
+      ho += dq; wo += dr;
+      if (wo >= P.Wo) { wo -= P.Wo; ++ho; }
     }
   }
 }
@@ -592,7 +598,7 @@ int launch_se_scale(void* d_y, const void* d_gates, int batch, int npix, int C, 
 int launch_stem(const float* d_feats, int batch, const StemParams& P, void* d_out, int sm_count,
                 cudaStream_t st) {
   if (batch == 0) return KWS_OK;
-  const size_t smem = (size_t)(((P.H * P.W + 3) & ~3) + 9 * kStemC + kStemC) * 4;
+  const size_t smem = (size_t)((((P.H + 2) * (P.W + 2) + 3) & ~3) + 9 * kStemC + kStemC) * 4;
   const int grid = batch < sm_count * 4 ? batch : sm_count * 4;
   KWS_CUDA_CHECK(launch_pdl(stem_conv_kernel, dim3(grid), dim3(kStemThreads), smem, st, d_feats, batch, P,
                             static_cast<uint16_t*>(d_out)));

@@ -12,13 +12,14 @@ namespace {
 
 
 struct SmemLayout {
-  uint32_t stage_bytes, bar_off, total;
+  uint32_t stage_bytes, bar_off, bias_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int block_n, int block_k, int stages) {
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int block_k, int stages, int N) {
   SmemLayout L;
   L.stage_bytes = (uint32_t)(kGemmBlockM + block_n) * block_k * 2;     // A tile then W tile, both multiples of 512 B
   L.bar_off = (L.stage_bytes * stages + 1023) & ~1023u;
-  L.total = L.bar_off + 8 * (2 * kGemmMaxStages + 4) + 16;
+  L.bias_off = L.bar_off + 8 * (2 * kGemmMaxStages + 4) + 16;          // float s_bias[N rounded up to 16]
+  L.total = L.bias_off + (uint32_t)((N + 15) & ~15) * 4;
   return L;
 }
 
@@ -53,7 +54,7 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
 // ACT / RES / GAP / F32 / BF are compile-time for the configurations the embedding tower uses (-1 = read `ep`).
 template <int ACT, int RES, int GAP, int F32, int BF>
 __device__ __forceinline__ void epilogue_chunk(const GemmShape& sh, const GemmEpilogue& ep, const uint32_t (&r)[16],
-                                               int n0, int row, bool row_ok, int lane) {
+                                               uint32_t s_bias_addr, int n0, int row, bool row_ok, int lane) {
   const int act = ACT >= 0 ? ACT : ep.act;
   const bool has_res = RES >= 0 ? (RES != 0) : (ep.residual != nullptr);
   const bool gap4 = GAP >= 0 ? (GAP != 0) : (ep.gap4 != 0);
@@ -63,12 +64,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmShape& sh, const GemmEp
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-  if (ep.bias) {                                      // same addresses for the whole warp: broadcast L1 hits
-    const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
-#pragma unroll
+  {                                                   // bias: the whole vector sits in smem (zeros without a bias);
+#pragma unroll                                        // warp-uniform 16-byte shared loads (broadcast)
     for (int q = 0; q < 4; ++q) {
-      if (q >= 2 && !full) break;
-      const float4 b = __ldg(bp + q);
+      float4 b;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(s_bias_addr + (uint32_t)(n0 + 4 * q) * 4u));
       v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
     }
   }
@@ -133,13 +134,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const GemmShape sh, const GemmEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const SmemLayout L = smem_layout(sh.block_n, sh.block_k, sh.stages);
+  const SmemLayout L = smem_layout(sh.block_n, sh.block_k, sh.stages, sh.N);
   const uint32_t a_bytes = (uint32_t)kGemmBlockM * sh.block_k * 2;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + kGemmMaxStages;
   uint64_t* tmem_full = empty_bar + kGemmMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + L.bias_off);
+  // the bias vector (a constant of the layer: safe to read before the dependency wait below) goes to smem once
+  for (int i = threadIdx.x; i < ((sh.N + 15) & ~15); i += kGemmThreads) s_bias[i] = (ep.bias && i < sh.N) ? __ldg(ep.bias + i) : 0.0f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int block_n = sh.block_n, stages = sh.stages;
@@ -233,6 +237,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int half = (warp - 2) >> 2;                     // which of the two warps of this quarter (chunk parity)
     int acc = 0;
     uint32_t acc_phase = 0;
+    const uint32_t s_bias_addr = ptx::smem_u32(s_bias);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_t = tile / sh.n_tiles, n_t = tile - m_t * sh.n_tiles;
       const int row = m_t * kGemmBlockM + q * 32 + lane;
@@ -251,12 +256,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ptx::tmem_ld_wait();
           const int c1 = c0 + 32;
           if (c1 < n_lim) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c1, rb);
-          epilogue_chunk<ACT, RES, GAP, F32, BF>(sh, ep, ra, n_tile0 + c0, row, row_ok, lane);
+          epilogue_chunk<ACT, RES, GAP, F32, BF>(sh, ep, ra, s_bias_addr, n_tile0 + c0, row, row_ok, lane);
           if (c1 >= n_lim) break;
           ptx::tmem_ld_wait();
           c0 = c1 + 32;
           if (c0 < n_lim) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, ra);
-          epilogue_chunk<ACT, RES, GAP, F32, BF>(sh, ep, rb, n_tile0 + c1, row, row_ok, lane);
+          epilogue_chunk<ACT, RES, GAP, F32, BF>(sh, ep, rb, s_bias_addr, n_tile0 + c1, row, row_ok, lane);
           if (c0 >= n_lim) break;
         }
       }
@@ -374,12 +379,12 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   const size_t budget = ((num_kb <= 2 && sh.block_n <= 128) || (many_tiles && num_kb <= 4)) ? 110 * 1024 : 220 * 1024;
   sh.acc_stages = 2;
   int stages = kGemmMaxStages;
-  while (stages > 2 && smem_layout(sh.block_n, sh.block_k, stages).total + 1024 > budget) --stages;
+  while (stages > 2 && smem_layout(sh.block_n, sh.block_k, stages, N).total + 1024 > budget) --stages;
   const int useful = num_kb * (tiles_per_cta < 8 ? tiles_per_cta : 8) + 1;
   if (stages > useful) stages = useful;
   if (stages < 2) stages = 2;
   sh.stages = stages;
-  const size_t smem = smem_layout(sh.block_n, sh.block_k, sh.stages).total + 1024;
+  const size_t smem = smem_layout(sh.block_n, sh.block_k, sh.stages, N).total + 1024;
   KWS_REQUIRE(smem <= 227 * 1024, "gemm: tile configuration does not fit shared memory");
 
   CUtensorMap ta, tb;
