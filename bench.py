@@ -326,19 +326,23 @@ def run_ours(args, rank, local_rank, world):
         shares = {k: round(a["ms"] / total, 4) for k, a in agg.items()}
         top = max(agg, key=lambda k: agg[k]["ms"])
         a = agg[top]
+        hbm_gbs = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+        roof = dict(kernel=top, bound="hbm", achieved=hbm_gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=hbm_gbs / peaks["hbm_gbs"],
+                    traffic=None, launches_per_step=a["launches"], avg_launch_ms=a["ms"] / a["launches"],
+                    peak_source=peaks["source"],
+                    note="all launches of the kernel in one step: sum of algorithmic bytes (operands + results of every "
+                         "launch, activations in 16 bit) / sum of launch durations")
         if top == "gemm_tcgen05_kernel":
-            ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
-            peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-            roof = dict(kernel=top, bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
-                        launches_per_step=a["launches"], avg_launch_ms=a["ms"] / a["launches"],
-                        peak_source=peaks["source"] + ", sustained 16-bit dense GEMM",
-                        note="all launches of the kernel in one step: sum of algorithmic FLOPs / sum of launch durations")
-        else:
-            ach = a["bytes"] / (a["ms"] * 1e-3) / 1e9
-            roof = dict(kernel=top, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
-                        traffic=None, launches_per_step=a["launches"], avg_launch_ms=a["ms"] / a["launches"],
-                        peak_source=peaks["source"],
-                        note="algorithmic activation bytes (input read + gated output write) of all launches / sum of durations")
+            # the dense contractions have two roofs; the binding one is the roof with the larger minimum time.  With
+            # K = 16 ... 1152 and M = batch x pixels the activation traffic, not the tensor pipe, is the tighter bound.
+            tf = a["flops"] / (a["ms"] * 1e-3) / 1e12
+            tpeak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+            tensor = dict(bound="tensor", achieved=tf, peak=tpeak, unit="TFLOP/s", frac=tf / tpeak)
+            if tensor["frac"] > roof["frac"]:
+                roof.update(tensor)
+                roof["other_roof"] = dict(bound="hbm", achieved=hbm_gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=hbm_gbs / peaks["hbm_gbs"])
+            else:
+                roof["other_roof"] = tensor
         roof["per_kernel_ms"] = {k: round(v["ms"], 4) for k, v in agg.items()}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload

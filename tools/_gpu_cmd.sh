@@ -1,2 +1,8 @@
-timeout 900 python -m pytest tests/test_embed_gpu.py tests/test_gemm_gpu.py -x -q -m gpu -s 2>&1 | grep -v "^block\|^stem\|^dense\|^top" | tail -6
-timeout 200 python tools/ab.py bias_smem_stem 2>&1 | head -3
+timeout 300 python tools/sweep.py 2>&1 | grep -v "all ops"
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_ab.json 2> gpurun_out/bench_ab.err; tail -3 gpurun_out/bench_ab.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_ab.json'))
+print({k:d[k] for k in ('value','ms_per_step','overlapped','e2e','finetune')})
+print(d['roofline'])
+PY

@@ -11,10 +11,10 @@ fe = MicroFrontend()
 w = W.random_init(0, randomize_bn=True, residual_gamma_scale=0.3)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 kinds = {0: "stem", 1: "gemm", 2: "dwse"}
-for B in (1024, 4096):
+for B in (1024,):
     pcm = torch.from_numpy(np.tile(synthetic_pcm(256, cfg_id=2), (-(-B // 256), 1))[:B]).cuda()
     feats = fe.forward(pcm)
-    for chunk, late in ((256, 2048), (128, 2048), (512, 2048), (256, 512), (1024, 4096)):
+    for chunk, late in ((256, 2048), (512, 1024), (512, 4096), (1024, 512), (1024, 1024), (1024, 4096)):
         m = EmbeddingModel(w, chunk=chunk)
         m.set_chunk_late(late)
         out = torch.empty((B, 1024), device="cuda")
