@@ -45,6 +45,53 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def host_threads() -> int:
+    """Host threads this process may really use: the affinity mask, capped by the cgroup CPU quota (a container that
+    sees 128 CPUs but owns a 16-CPU quota is slower with 128 threads than with 16)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = int(q) / int(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota:
+        n = min(n, max(1, int(quota + 0.999)))
+    return max(1, n)
+
+
+def bounded_cpu_sample(step_fn, max_clips: int, budget_s: float, n_steps: int, probe: int = 32) -> int:
+    """Clips per CPU step such that n_steps steps take about budget_s: times a small probe first."""
+    probe = min(probe, max_clips)
+    step_fn(probe)                                   # page-in / thread-pool start-up
+    t0 = time.perf_counter()
+    step_fn(probe)
+    per_clip = (time.perf_counter() - t0) / probe
+    n = int(budget_s / max(n_steps, 1) / max(per_clip, 1e-9))
+    return int(max(probe, min(max_clips, n)))
+
+
+def load_traffic():
+    """DRAM bytes per launch of each kernel, measured by ncu (tools/traffic_from_ncu.py -> profiles/*_traffic.json).
+    bench.py never runs under a profiler; it only quotes the committed capture, and says which."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        return json.load(f), os.path.relpath(files[-1], ROOT)
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -95,23 +142,24 @@ def run_reference(args, rank, world):
     from multilingual_kws_b200.synthetic import synthetic_pcm
     from oracle import effnet_oracle as EO
     from oracle.frontend_oracle import FrontendOracle
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
-    B = min(args.batch, args.ref_sample)
-    pcm = synthetic_pcm(B, cfg_id=2)
+    pcm_all = synthetic_pcm(min(args.batch, args.ref_sample), cfg_id=2)
     w = W.random_init(0, randomize_bn=True)
     orc = FrontendOracle()
 
-    def step():
-        feats = orc.features(pcm, threads=cores)
+    def run(n):
+        feats = orc.features(pcm_all[:n], threads=cores)
         with torch.no_grad():
             return EO.forward(w, feats)
 
+    # bounded sample: the whole --steps/--warmup run has to end within a few minutes on any host
+    B = bounded_cpu_sample(run, pcm_all.shape[0], args.ref_budget_s, args.steps + args.warmup)
     for _ in range(args.warmup):
-        step()
+        run(B)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        run(B)
     dt = (time.perf_counter() - t0) / args.steps
     v = B / dt
     sample = f"{B} synthetic clips per step (of the {args.batch}-clip workload), frontend + embedding, {cores} host threads"
@@ -344,22 +392,33 @@ def run_ours(args, rank, local_rank, world):
             else:
                 roof["other_roof"] = tensor
         roof["per_kernel_ms"] = {k: round(v["ms"], 4) for k, v in agg.items()}
+        tr, tr_file = load_traffic()
+        if tr and top in tr["kernels"] and tr.get("batch") == B:
+            t_ = tr["kernels"][top]
+            roof["traffic"] = t_["dram_bytes_per_launch"]
+            roof["traffic_note"] = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the {t_['launches']} launches of "
+                                    f"one forward pass at batch {B}, from the committed ncu capture {tr_file}")
+            roof["algorithmic_bytes_per_launch"] = a["bytes"] / a["launches"]
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import effnet_oracle as EO
         from oracle.frontend_oracle import FrontendOracle
-        cores = os.cpu_count() or 1
+        cores = host_threads()
         torch.set_num_threads(cores)
-        nb = min(B, args.ref_sample)
         orc = FrontendOracle()
+
+        def cpu_run(n):
+            f_ = orc.features(pcm_host[:n], threads=cores)
+            with torch.no_grad():
+                return f_, EO.forward(weights, f_)
+
+        nb = bounded_cpu_sample(cpu_run, min(B, args.ref_sample), 15.0, 3)       # ~5 s per repetition at most
         t0 = time.perf_counter()
         reps = 0
-        while reps < 2 or time.perf_counter() - t0 < 10.0:
-            f = orc.features(pcm_host[:nb], threads=cores)
-            with torch.no_grad():
-                ref_emb = EO.forward(weights, f)
+        while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+            f, ref_emb = cpu_run(nb)
             reps += 1
         dt = (time.perf_counter() - t0) / reps
         cpu = {"value": nb / dt, "unit": UNIT, "cores": cores, "kind": "port",
@@ -425,6 +484,8 @@ def main():
     ap.add_argument("--chunk-late", type=int, default=4096, help="clips per pass for the late (small-activation) layers")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--ref-sample", type=int, default=1024, help="clips per reference / cpu_baseline step")
+    ap.add_argument("--ref-budget-s", type=float, default=120.0,
+                    help="wall-clock budget of the whole --impl reference run (the per-step sample is sized to fit)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying the CUDA graph")
     args = ap.parse_args()
