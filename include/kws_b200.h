@@ -144,6 +144,24 @@ int kws_head_apply_adam(kws_head_t* h, const float* d_flat, float lr, void* stre
 int kws_head_get_params(const kws_head_t* h, float* host_out);
 int kws_head_reset_optimizer(kws_head_t* h);
 
+/* ---------------------------------------------------------------------------------------------
+ * Streaming post-processor — replaces the per-window Python loop
+ *   for ix, offset in enumerate(range(0, audio_data_end, clip_stride_samples)):
+ *       recognize_commands.process_latest_result(inferences[ix], current_time_ms, recognize_element)
+ * of multilingual_kws/embedding/batch_streaming_analysis.py:131-163, i.e.
+ * SingleTargetRecognizeCommands.process_latest_result (single_target_recognize_commands.py:94-207), for every
+ * detection threshold of a sweep at once.  d_probs float32 [n_windows, n_labels] (the softmax rows, left on the
+ * device by the head), d_times_ms int64 [n_windows] ascending (the reference raises ValueError on out-of-order
+ * input; the caller checks).  Outputs: d_scores double [n_windows] = recognize_element.score at every step
+ * (bit-identical: same float64 operation order), d_valid uint8 [n_windows] = 0 where the reference bails out
+ * ("too few results"), d_found_idx int32 [n_thresholds, max_found] = window indices of the new non-silence
+ * commands, d_found_count int32 [n_thresholds] (may exceed max_found: rerun with a larger buffer).
+ * ------------------------------------------------------------------------------------------- */
+int kws_stream_detect(const float* d_probs, int n_windows, int n_labels, int target_id, const int64_t* d_times_ms,
+                      double average_window_duration_ms, double suppression_ms, int minimum_count,
+                      const double* d_thresholds, int n_thresholds, double* d_scores, uint8_t* d_valid,
+                      int32_t* d_found_idx, int32_t* d_found_count, int max_found, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

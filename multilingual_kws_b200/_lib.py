@@ -57,6 +57,8 @@ SIGNATURES = {
     "kws_head_apply_adam": (c_int, [c_void_p, c_void_p, c_float, c_void_p]),
     "kws_head_get_params": (c_int, [c_void_p, c_void_p]),
     "kws_head_reset_optimizer": (c_int, [c_void_p]),
+    "kws_stream_detect": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_double, ctypes.c_double, c_int, c_void_p,
+                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "kws_frontend_stream": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_int64, c_float, c_void_p,
                                     c_void_p, c_int, c_void_p]),
 }

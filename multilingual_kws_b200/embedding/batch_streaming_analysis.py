@@ -4,8 +4,9 @@
 The reference slides a 1 s window with a 20 ms stride over the wav and calls the CPU frontend once per window
 from a Python loop (:108-115) before one ``model.predict``.  Here the whole signal goes to the GPU once, the
 per-frame frontend work is computed once per 20 ms frame and shared by all windows (bit-identical, see
-kws_frontend_stream), and windows are embedded + classified in large batches.  Ground-truth accuracy bookkeeping
-(accuracy_utils / tpr_fpr in the reference) is out of scope; detections are returned in the same structure.
+kws_frontend_stream), windows are embedded + classified in large batches, and the post-processing recurrence runs
+on the device for all detection thresholds at once (kws_stream_detect) when the softmax rows were produced there.
+Ground-truth bookkeeping follows the reference (accuracy_utils.StreamingAccuracyStats), results keep its structure.
 """
 from __future__ import annotations
 
@@ -18,7 +19,8 @@ import numpy as np
 import torch
 
 from . import input_data
-from .single_target_recognize_commands import detect_stream
+from .accuracy_utils import StreamingAccuracyStats
+from .single_target_recognize_commands import detect_stream, detect_stream_device
 from ..frontend import FEATURE_SCALE, float_audio_to_int16_np
 
 
@@ -51,7 +53,7 @@ class StreamTarget:
 
 
 def stream_inferences(model, model_settings, audio: np.ndarray, sample_rate: int, clip_duration_ms: int,
-                      clip_stride_ms: int, window_batch: int = 8192) -> np.ndarray:
+                      clip_stride_ms: int, window_batch: int = 8192, keep_on_device: bool = False):
     """softmax rows [W, n_labels] for every window offset in range(0, len - clip, stride)
     (batch_streaming_analysis.py:66-117; the chunk branches there add up to the un-chunked result)."""
     clip = int(clip_duration_ms * sample_rate / 1000)
@@ -61,13 +63,14 @@ def stream_inferences(model, model_settings, audio: np.ndarray, sample_rate: int
     W = fe.stream_num_windows(pcm.numel(), clip, stride)
     n_labels = model.head.classes if hasattr(model, "head") else model.output_dim
     if W <= 0:
-        return np.zeros((0, n_labels), np.float32)
+        return torch.zeros((0, n_labels), device="cuda") if keep_on_device else np.zeros((0, n_labels), np.float32)
     st = fe.stream_prepare(pcm)
     outs = []
     for w0 in range(0, W, window_batch):
         feats = st.windows(clip, stride, w0, min(window_batch, W - w0), FEATURE_SCALE)
-        outs.append(model.forward_device(feats).cpu())
-    return torch.cat(outs).numpy()
+        outs.append(model.forward_device(feats).clone())
+    probs = torch.cat(outs)
+    return probs if keep_on_device else probs.cpu().numpy()
 
 
 def calculate_streaming_accuracy(model, model_settings, flag_list, existing_inferences=None):
@@ -81,18 +84,37 @@ def calculate_streaming_accuracy(model, model_settings, flag_list, existing_infe
     clip_duration_samples = int(f0.clip_duration_ms * sample_rate / 1000)
     clip_stride_samples = int(f0.clip_stride_ms * sample_rate / 1000)
     audio_data_end = audio.shape[0] - clip_duration_samples
+    times = [int(o * 1000 / sample_rate) for o in range(0, audio_data_end, clip_stride_samples)]
+    device_probs = None
     if existing_inferences is not None:
         inferences = existing_inferences
     else:
-        inferences = stream_inferences(model, model_settings, audio, sample_rate, f0.clip_duration_ms, f0.clip_stride_ms)
-    times = [int(o * 1000 / sample_rate) for o in range(0, audio_data_end, clip_stride_samples)]
+        device_probs = stream_inferences(model, model_settings, audio, sample_rate, f0.clip_duration_ms,
+                                         f0.clip_stride_ms, keep_on_device=True)
+        inferences = device_probs.cpu().numpy()
     results = []
     for FLAGS in flag_list:
         res_thresh = {}
+        if device_probs is not None:      # softmax rows are on the GPU: the whole threshold sweep is one launch
+            sweep = detect_stream_device(device_probs[:len(times)], times, FLAGS.labels(), FLAGS.average_window_duration_ms,
+                                         FLAGS.detection_thresholds, FLAGS.suppression_ms, FLAGS.minimum_count, target_id=2)
         for threshold in FLAGS.detection_thresholds:
-            found = detect_stream(inferences, times, FLAGS.labels(), FLAGS.average_window_duration_ms, threshold,
-                                  FLAGS.suppression_ms, FLAGS.minimum_count, target_id=2)
-            res_thresh[threshold] = ([[w, t] for w, t, _ in found], [[w, t, s] for w, t, s in found])
+            if device_probs is not None:
+                found = sweep[threshold]
+            else:                         # caller-supplied host matrix (reference: existing_inferences)
+                found = detect_stream(inferences, times, FLAGS.labels(), FLAGS.average_window_duration_ms, threshold,
+                                      FLAGS.suppression_ms, FLAGS.minimum_count, target_id=2)
+            all_found_words = [[w, t] for w, t, _ in found]
+            # accuracy statistics, updated detection by detection as the reference does (:150-170)
+            stats = StreamingAccuracyStats(target_keyword=FLAGS.target_keyword)
+            stats.read_ground_truth_file(FLAGS.ground_truth)
+            for n in range(1, len(all_found_words) + 1):
+                stats.calculate_accuracy_stats(all_found_words[:n], all_found_words[n - 1][1], FLAGS.time_tolerance_ms)
+                stats.delta()
+            print(f"results for {threshold:0.2f}")
+            stats.calculate_accuracy_stats(all_found_words, -1, FLAGS.time_tolerance_ms)
+            stats.print_accuracy_stats()
+            res_thresh[threshold] = (all_found_words, [[w, t, s] for w, t, s in found])
         results.append((FLAGS, res_thresh))
     return results, inferences
 

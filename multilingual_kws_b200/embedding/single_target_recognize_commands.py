@@ -92,3 +92,56 @@ def detect_stream(inferences: np.ndarray, times_ms: Sequence[int], labels: Seque
         if el.is_new_command and el.found_command != SILENCE:
             found.append((el.found_command, int(t), float(el.score)))
     return found
+
+
+def detect_stream_device(inferences, times_ms: Sequence[int], labels: Sequence[str], average_window_duration_ms,
+                         detection_thresholds: Sequence[float], suppression_ms, minimum_count, target_id=2,
+                         return_scores: bool = False):
+    """The same recurrence on the GPU for a whole sweep of thresholds in one call (``kws_stream_detect``,
+    csrc/stream_detect.cu): `inferences` is the float32 [W, n_labels] softmax matrix (a CUDA tensor as the head left
+    it, or anything `torch.as_tensor` accepts, which is uploaded).  Returns {threshold: [(word, time_ms, score), ...]}
+    — per threshold exactly what `detect_stream` returns, scores bit-identical (same float64 operation order) — and,
+    with return_scores, the per-step `recognize_element.score` array as well.  No CPU fallback."""
+    import torch
+
+    from .. import _lib
+    labels = list(labels)
+    if labels[target_id] == SILENCE:
+        raise ValueError("the target label must not be the silence label")
+    probs = torch.as_tensor(inferences)
+    if probs.dtype != torch.float32:
+        probs = probs.float()
+    probs = probs.cuda().contiguous()
+    if probs.dim() != 2 or probs.shape[1] != len(labels):
+        raise ValueError("The results for recognition should contain {} elements, but there are {} produced".format(
+            len(labels), probs.shape[-1]))
+    W = probs.shape[0]
+    t_host = np.asarray(times_ms, dtype=np.int64)
+    if t_host.shape != (W,):
+        raise ValueError(f"need one timestamp per inference row ({W}), got {t_host.shape}")
+    if W > 1 and (np.diff(t_host) < 0).any():
+        i = int(np.argmax(np.diff(t_host) < 0)) + 1
+        raise ValueError("Results must be fed in increasing time order, but receive a timestamp of {}, which was "
+                         "earlier than the previous one of {}".format(int(t_host[i]), int(t_host[i - 1])))
+    thr_host = np.asarray(list(detection_thresholds), dtype=np.float64)
+    dev = probs.device
+    times = torch.from_numpy(t_host).to(dev)
+    thr = torch.from_numpy(thr_host).to(dev)
+    scores = torch.empty(W, dtype=torch.float64, device=dev)
+    valid = torch.empty(W, dtype=torch.uint8, device=dev)
+    cap = max(W, 1)
+    found_idx = torch.empty((len(thr_host), cap), dtype=torch.int32, device=dev)
+    found_cnt = torch.empty(len(thr_host), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().kws_stream_detect(
+        probs.data_ptr(), W, probs.shape[1], int(target_id), times.data_ptr(), float(average_window_duration_ms),
+        float(suppression_ms), int(minimum_count), thr.data_ptr(), len(thr_host), scores.data_ptr(), valid.data_ptr(),
+        found_idx.data_ptr(), found_cnt.data_ptr(), cap, _lib.current_stream_ptr()), "kws_stream_detect")
+    counts = found_cnt.cpu().numpy()
+    idx_host = found_idx.cpu().numpy()
+    scores_host = scores.cpu().numpy()
+    word = labels[target_id]
+    out = {}
+    for k, th in enumerate(detection_thresholds):
+        ids = idx_host[k, :counts[k]]
+        out[th] = [(word, int(t_host[i]), float(scores_host[i])) for i in ids]
+    return (out, scores_host) if return_scores else out
