@@ -148,7 +148,9 @@ def test_streaming_matches_per_window_recompute(world, tmp_path):
     input_data.encode_wav(wav, x.astype(np.float64) / 32768.0)
     model = FewShotModel(EmbeddingModel({k: v for k, v in world["w"].items() if not k.startswith("dense_3")}),
                          Head.keras_init(1024, 18, 3, seed=1))
-    flags = [sa.StreamFlags(wav=wav, ground_truth="", target_keyword="tiempo", detection_thresholds=[0.3, 0.9],
+    gt = tmp_path / "gt.txt"
+    gt.write_text("tiempo,1200\n_unknown_,2600\n")
+    flags = [sa.StreamFlags(wav=wav, ground_truth=str(gt), target_keyword="tiempo", detection_thresholds=[0.3, 0.9],
                             clip_stride_ms=100)]
     results, inferences = sa.calculate_streaming_accuracy(model, s, flags)
     offsets = list(range(0, T - 16000, 1600))
@@ -159,7 +161,7 @@ def test_streaming_matches_per_window_recompute(world, tmp_path):
     (fl, res), = results
     assert set(res) == {0.3, 0.9} and all(len(v) == 2 for v in res.values())
     r2, _ = sa.calculate_streaming_accuracy(model, s, flags, existing_inferences=inferences)
-    assert r2[0][1] == res
+    assert r2[0][1] == res            # device post-processor (first call) == host recogniser (existing_inferences)
 
 
 def test_host_pipeline_matches_direct_path(world):
