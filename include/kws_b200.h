@@ -162,6 +162,31 @@ int kws_stream_detect(const float* d_probs, int n_windows, int n_labels, int tar
                       const double* d_thresholds, int n_thresholds, double* d_scores, uint8_t* d_valid,
                       int32_t* d_found_idx, int32_t* d_found_count, int max_found, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Waveform augmentation of the fine-tune input pipeline — replaces, per batch, the tf.data map
+ *   ds.map(self.augment) -> ds.map(self.get_spectrogram_and_label_id) -> ds.map(self.map_spec_aug)
+ * of multilingual_kws/embedding/input_data.py:447-471, i.e. random_timeshift (:243-267),
+ * random_background_sample (:227-241), add_background (:141-157), the branches of augment (:275-304), the int16
+ * cast at :23 and spec_augment (:306-364).  Random decisions are drawn by the caller (one kws_aug_item per output
+ * clip); samples stay on the device: d_fg int16 [n_fg, fg_stride] holds the source clips (decode_wav output x 32768,
+ * exact), d_bg int16 [n_bg, bg_stride] the zero-padded background recordings; both 16-byte aligned with strides that
+ * are multiples of 8.  d_pcm_out int16 [batch, n_samples] feeds kws_frontend_forward; d_audio_out (optional, may be
+ * NULL) receives the float32 waveform before the int16 cast.
+ *   mode 0: out[i] = fg[i - shift] (zero outside the clip)                       plain / time-shifted / "unknown" clip
+ *   mode 1: out[i] = bg[bg_offset + i] * volume                                  "silence" sample
+ *   mode 2: out[i] = clip(bg[bg_offset + i] * (rms_fg / rms_bg) * volume + fg[i - shift], -1, 1)   background mix
+ * kws_spec_mask zeroes, in place, up to two frequency bands and two time bands per clip of d_feats
+ * [batch, frames, channels]; d_bands int32 [batch, 8] = (f_start, f_size) x 2, (t_start, t_size) x 2, size 0 = unused.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct kws_aug_item {
+  int32_t mode, fg_index, shift, bg_index, bg_offset;
+  float volume;
+  int32_t reserved[2];
+} kws_aug_item;
+int kws_augment_pcm(const int16_t* d_fg, int n_fg, int fg_stride, const int16_t* d_bg, int n_bg, int bg_stride,
+                    const void* d_plan, int batch, int n_samples, int16_t* d_pcm_out, float* d_audio_out, void* stream);
+int kws_spec_mask(float* d_feats, int batch, int frames, int channels, const int32_t* d_bands, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,9 @@ SIGNATURES = {
     "kws_head_reset_optimizer": (c_int, [c_void_p]),
     "kws_stream_detect": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_double, ctypes.c_double, c_int, c_void_p,
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "kws_augment_pcm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                c_void_p]),
+    "kws_spec_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "kws_frontend_stream": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_int64, c_float, c_void_p,
                                     c_void_p, c_int, c_void_p]),
 }

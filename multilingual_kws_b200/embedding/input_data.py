@@ -21,6 +21,7 @@ from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+from ..augment import AUG_ITEM, MODE_CLIP, MODE_MIX, MODE_SILENCE, DeviceAugmenter, plan_item, spec_mask_
 from ..frontend import FEATURE_SCALE, MicroFrontend, float_audio_to_int16_np
 
 SILENCE_LABEL = "_silence_"
@@ -169,11 +170,14 @@ def standard_microspeech_model_settings(label_count: int):
 
 
 def add_background(foreground_audio, background_audio, background_volume):
-    """reference input_data.py:141-157 (float32 arithmetic)."""
+    """reference input_data.py:141-157: float32 arithmetic throughout; the two mean squares are float32 squares
+    accumulated in float64 and rounded once (TF's reduce_mean sums float32 in an unspecified tree order, so its last
+    bit is not reproducible anyway) — the same definition the device kernel uses (csrc/augment.cu), which makes the
+    host mirror and the GPU path agree bit for bit."""
     fg = np.asarray(foreground_audio, np.float32)
     bg = np.asarray(background_audio, np.float32)
-    foreground_rms = np.sqrt(np.mean(np.square(fg), dtype=np.float32))
-    background_rms = np.sqrt(np.mean(np.square(bg), dtype=np.float32))
+    foreground_rms = np.sqrt(np.float32(np.mean(np.square(fg), dtype=np.float64)))
+    background_rms = np.sqrt(np.float32(np.mean(np.square(bg), dtype=np.float64)))
     snr_scaling = np.float32(foreground_rms / background_rms) if background_rms > 0 else np.float32(0.0)
     bg_add = bg * snr_scaling * np.float32(background_volume) + fg
     return np.clip(bg_add, -1.0, 1.0).astype(np.float32)
@@ -240,7 +244,11 @@ class _Dataset:
 
     def _finish(self, waves: List[np.ndarray], labels: List[int]):
         o = self.owner
-        specs = to_micro_spectrogram(o.model_settings, torch.from_numpy(np.stack(waves)))    # [n, T, F] on the GPU
+        if o.device_augment:      # elements are augmentation plan items: samples are mixed on the GPU (augment.py)
+            pcm = o._augmenter().run(np.stack(waves).astype(AUG_ITEM, copy=False))
+            specs = _frontend_for(o.model_settings).forward(pcm, out_scale=FEATURE_SCALE)
+        else:
+            specs = to_micro_spectrogram(o.model_settings, torch.from_numpy(np.stack(waves)))    # [n, T, F] on the GPU
         if self.training:
             specs = o._spec_augment_batch(specs)
         return specs[..., None], torch.as_tensor(np.asarray(labels, np.int64))
@@ -271,7 +279,13 @@ class _Dataset:
 class AudioDataset:
     def __init__(self, model_settings, commands, background_data_dir, unknown_files, time_shift_ms=100,
                  background_frequency=0.8, background_volume_range=0.1, silence_percentage=10.0,
-                 unknown_percentage=10.0, spec_aug_params=SpecAugParams(), seed=None) -> None:
+                 unknown_percentage=10.0, spec_aug_params=SpecAugParams(), seed=None, device_augment=False) -> None:
+        """Arguments as the reference (:173-187).  device_augment=True (not in the reference) keeps the decoded clips
+        in an int16 bank on the GPU and runs time shift / background mix / int16 cast / spec-augment masks there
+        (augment.py); the random draws, and therefore the batches, are identical to the host path for the same seed."""
+        self.device_augment = bool(device_augment)
+        self._aug = None
+        self._bank_rows = {}
         self.model_settings = model_settings
         self.get_background_data(background_data_dir)
         self.max_time_shift_samples = self.timeshift_samples(time_shift_ms=time_shift_ms)
@@ -329,17 +343,25 @@ class AudioDataset:
             audio = add_background(audio, self.random_background_sample(), background_volume)
         return audio, label
 
-    def _spec_aug_mask(self, time_max: int, freq_max: int) -> np.ndarray:
-        """One draw of reference spec_augment (:306-364) as a multiplicative 0/1 mask [T, F]."""
+    def _spec_aug_bands(self, time_max: int, freq_max: int):
+        """One draw of reference spec_augment (:306-364): ([(f_start, f_size), ...], [(t_start, t_size), ...])."""
         p = self.spec_aug_params
-        mask = np.ones((time_max, freq_max), np.float32)
+        fbands, tbands = [], []
         for _ in range(int(self.gen.integers(0, p.frequency_n_range + 1))):
             size = int(self.gen.integers(1, p.frequency_max_px + 1))
-            start = int(self.gen.integers(0, freq_max - size))
-            mask[:, start:start + size] = 0.0
+            fbands.append((int(self.gen.integers(0, freq_max - size)), size))
         for _ in range(int(self.gen.integers(0, p.time_n_range + 1))):
             size = int(self.gen.integers(1, p.time_max_px + 1))
-            start = int(self.gen.integers(0, time_max - size))
+            tbands.append((int(self.gen.integers(0, time_max - size)), size))
+        return fbands, tbands
+
+    def _spec_aug_mask(self, time_max: int, freq_max: int) -> np.ndarray:
+        """The same draw as a multiplicative 0/1 mask [T, F]."""
+        fbands, tbands = self._spec_aug_bands(time_max, freq_max)
+        mask = np.ones((time_max, freq_max), np.float32)
+        for start, size in fbands:
+            mask[:, start:start + size] = 0.0
+        for start, size in tbands:
             mask[start:start + size, :] = 0.0
         return mask
 
@@ -354,11 +376,58 @@ class AudioDataset:
 
     def _spec_augment_batch(self, specs: torch.Tensor) -> torch.Tensor:
         n, t, f = specs.shape
+        p = self.spec_aug_params
+        if self.device_augment and p.frequency_n_range <= 2 and p.time_n_range <= 2:
+            bands = np.zeros((n, 8), np.int32)       # 16 bytes of plan per clip instead of a [T, F] float mask
+            for i in range(n):
+                if self.gen.uniform(0, 1) < (p.percentage / 100):
+                    fb, tb = self._spec_aug_bands(t, f)
+                    bands[i, :2 * len(fb)] = np.asarray(fb, np.int32).reshape(-1)
+                    bands[i, 4:4 + 2 * len(tb)] = np.asarray(tb, np.int32).reshape(-1)
+            return spec_mask_(specs.contiguous(), bands)
         masks = np.ones((n, t, f), np.float32)
         for i in range(n):
             if self.gen.uniform(0, 1) < (self.spec_aug_params.percentage / 100):
                 masks[i] = self._spec_aug_mask(t, f)
         return specs * torch.from_numpy(masks).to(specs.device)
+
+    # ---- device path: the same decisions as a plan item (augment.py), same order of random draws as augment()
+    def _augmenter(self) -> DeviceAugmenter:
+        if self._aug is None:
+            self._aug = DeviceAugmenter(self.model_settings["desired_samples"], self.background_data)
+        return self._aug
+
+    def _bank_row(self, file_path) -> int:
+        """Row of the device clip bank holding decode_audio(file_path); decoded and uploaded on first use."""
+        key = os.fspath(file_path)
+        row = self._bank_rows.get(key)
+        if row is None:
+            row = self._bank_rows[key] = self._augmenter().clips.add(self.decode_audio(key))
+        return row
+
+    def _draw_timeshift(self) -> int:
+        return int(self.gen.integers(-self.max_time_shift_samples, self.max_time_shift_samples))
+
+    def _draw_background(self):
+        background_index = int(self.gen.integers(0, self.background_sizes.shape[0]))
+        wav_length = int(self.background_sizes[background_index])
+        return background_index, int(self.gen.integers(0, wav_length - self.model_settings["desired_samples"]))
+
+    def augment_plan(self, fg_row: int, label):
+        shift = self._draw_timeshift() if self.max_time_shift_samples > 0 else 0
+        if self.gen.uniform(0, 1) < (self.silence_percentage / 100):
+            volume = self.gen.uniform(0, 1)
+            bi, bo = self._draw_background()
+            return plan_item(MODE_SILENCE, bg_index=bi, bg_offset=bo, volume=volume), SILENCE_LABEL
+        if len(self.unknown_files) > 0 and self.gen.uniform(0, 1) < (self.unknown_percentage / 100):
+            row = self._bank_row(self.unknown_files[int(self.gen.integers(0, len(self.unknown_files)))])
+            shift = self._draw_timeshift() if self.max_time_shift_samples > 0 else 0
+            return plan_item(MODE_CLIP, fg_index=row, shift=shift), UNKNOWN_WORD_LABEL
+        if self.gen.uniform(0, 1) < self.background_frequency:
+            volume = self.gen.uniform(0, self.background_volume_range)
+            bi, bo = self._draw_background()
+            return plan_item(MODE_MIX, fg_index=fg_row, shift=shift, bg_index=bi, bg_offset=bo, volume=volume), label
+        return plan_item(MODE_CLIP, fg_index=fg_row, shift=shift), label
 
     # ---- data access (reference :375-434)
     def get_background_data(self, background_dir):
@@ -406,6 +475,17 @@ class AudioDataset:
     def _build(self, files, loader, is_training, extra=None) -> _Dataset:
         files = [os.fspath(f) for f in files]
 
+        def make_device():
+            label_of = self.get_label if loader == self.get_waveform_and_label else (lambda _f: str(self.commands[-1]))
+            for f in files:
+                item, label = plan_item(MODE_CLIP, fg_index=self._bank_row(f)), label_of(f)
+                if is_training:
+                    item, label = self.augment_plan(int(item["fg_index"]), label)
+                yield item, self.label_id(label)
+            if extra is not None:
+                for item, label in extra():
+                    yield item, self.label_id(label)
+
         def make():
             for f in files:
                 audio, label = loader(f)
@@ -415,6 +495,9 @@ class AudioDataset:
             if extra is not None:
                 for audio, label in extra():
                     yield np.asarray(audio, np.float32), self.label_id(label)
+
+        if self.device_augment:
+            make = make_device
 
         n = len(files) + (extra.n if extra is not None else 0)
         return _Dataset(self, make, n, is_training)
@@ -428,9 +511,16 @@ class AudioDataset:
         return self._build(files, self.get_waveform_and_label, is_training)
 
     def _random_silence(self):
+        if self.device_augment:
+            volume = self.gen.uniform(0, 1)
+            bi, bo = self._draw_background()
+            return plan_item(MODE_SILENCE, bg_index=bi, bg_offset=bo, volume=volume), SILENCE_LABEL
         return self.random_background_sample(self.gen.uniform(0, 1)), SILENCE_LABEL
 
     def _random_unknown(self):
+        if self.device_augment:
+            f = self.unknown_files[int(self.gen.integers(0, len(self.unknown_files)))]
+            return plan_item(MODE_CLIP, fg_index=self._bank_row(f)), UNKNOWN_WORD_LABEL
         return self.get_unknown(), UNKNOWN_WORD_LABEL
 
     def eval_with_silence_unknown(self, AUTOTUNE, files, label_from_parent_dir: bool):

@@ -134,6 +134,7 @@ def transfer_learn(
         unknown_files=unknown_files,
         unknown_percentage=UNKNOWN_PERCENTAGE,
         spec_aug_params=input_data.SpecAugParams(percentage=80),
+        device_augment=True,      # clips decoded once into a device bank; shift / mix / masks run on the GPU
     )
     init_train_ds = audio_dataset.init_single_target(AUTOTUNE, train_files, is_training=True)
     init_val_ds = audio_dataset.init_single_target(AUTOTUNE, val_files, is_training=False)
