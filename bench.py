@@ -247,7 +247,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- the same device-resident work with consecutive steps on alternating streams (what the host pipeline does):
     # late layers are latency-bound and leave SMs idle, early layers are throughput-bound, neighbouring steps fill
     # each other's gaps.  Region timing: first launch -> last kernel, L2 flushes included, / K.
-    n_str = 3
+    n_str = args.pipe_streams
     ov_streams = [torch.cuda.Stream(device=dev) for _ in range(n_str)]
     ov_bufs = [(torch.empty_like(feats), torch.empty_like(emb),
                 torch.empty(emb_model.workspace_bytes(B), dtype=torch.uint8, device=dev)) for _ in range(n_str)]
@@ -286,7 +286,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- e2e: public API, host buffers (pinned), H2D + D2H inside the timed region
     from multilingual_kws_b200.pipeline import EmbedPipeline
-    pipe = EmbedPipeline(fe, emb_model, n_samples=16000, sub_batch=B, depth=6, streams=3)
+    pipe = EmbedPipeline(fe, emb_model, n_samples=16000, sub_batch=B, depth=2 * args.pipe_streams, streams=args.pipe_streams)
     # host buffers: two input sets in write-combined pinned memory (kws_host_alloc), two pinned result buffers
     pcm_pinned2 = [pipe.alloc_input(B), pipe.alloc_input(B)]
     pcm_pinned2[0].copy_(torch.from_numpy(pcm_host))
@@ -443,7 +443,7 @@ def run_ours(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": args.dtype + " storage / tensor-core operands, fp32 accumulate; frontend int16/int32/uint64 fixed point",
             "data": "synthetic",
             "value_note": "value / ms_per_step: one step at a time on one stream (CUDA events around each step, L2 flushed "
-                          "before it); overlapped: K steps rotating over 3 streams, whole region / K, flushes included",
+                          "before it); overlapped: K steps rotating over the compute streams, whole region / K, flushes included",
             "overlapped": None if ms_overlap is None else {"value": world * B / (ms_overlap * 1e-3), "unit": UNIT,
                                                            "ms_per_step": ms_overlap, "streams": n_str},
             "config": {"workload": f"configs[1]: log-mel frontend + EfficientNet-B0 embedding forward, batch {B} x 1 s @ 16 kHz clips per GPU",
@@ -453,7 +453,7 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 32000, "d2h_bytes_per_step": B * emb_model.output_dim * 4,
                     "ms_per_step": ms_e2e,
                     "timing": "whole K-step region (first enqueue -> last download, L2 flushes included) / K; run_host "
-                              "enqueues only: upload i+1 / kernels i / download i-1 overlap, and consecutive steps rotate over three compute streams (6 device slots)",
+                              "enqueues only: upload i+1 / kernels i / download i-1 overlap, and consecutive steps rotate over the compute streams (2 device slots per stream)",
                     "ms_per_blocking_call_wall": ms_e2e_sync,
                     "host_buffers": "PCM in write-combined pinned memory (kws_host_alloc), results in pinned memory"},
             "gpu_launches": launches_per_step * args.steps,
@@ -487,6 +487,7 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=120.0,
                     help="wall-clock budget of the whole --impl reference run (the per-step sample is sized to fit)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipe-streams", type=int, default=3, help="compute streams the host pipeline / overlapped figure rotate over")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying the CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
