@@ -154,3 +154,50 @@ def test_missing_library_message(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libkws_b200.so")
     with pytest.raises(ImportError, match="no CPU fallback"):
         _lib.lib()
+
+
+def test_bench_cpu_leg_helpers():
+    """bench.py sizes its CPU legs from a probe so `--impl reference` ends within its budget on any host."""
+    import time
+    import bench
+    assert 1 <= bench.host_threads() <= (os.cpu_count() or 1)
+
+    def fake_step(n):
+        time.sleep(0.0005 * n)                       # 0.5 ms per clip
+
+    n = bench.bounded_cpu_sample(fake_step, max_clips=1024, budget_s=2.0, n_steps=4, probe=8)
+    assert 8 <= n <= 1024 and 0.25 * 1000 <= n <= 4 * 1000 or n == 1024      # ~1000 clips fit 0.5 s per step
+    assert bench.bounded_cpu_sample(fake_step, max_clips=16, budget_s=100.0, n_steps=1, probe=8) == 16
+    tr, name = bench.load_traffic()
+    assert tr is None or ("kernels" in tr and name.startswith("profiles"))
+
+
+def test_augment_plan_draws_match_host_augment(monkeypatch, tmp_path):
+    """Device-path plan items consume the random stream exactly like the host augment(): same seed -> same generator
+    state after every element, same labels (no GPU needed: the clip bank is stubbed)."""
+    from multilingual_kws_b200.embedding import input_data
+    rng = np.random.default_rng(0)
+    bgd = tmp_path / "_background_noise_"
+    bgd.mkdir()
+    input_data.encode_wav(str(bgd / "a.wav"), rng.normal(0, 0.05, 40000))
+    files = []
+    for i in range(6):
+        p = tmp_path / f"c{i}.wav"
+        input_data.encode_wav(str(p), rng.normal(0, 0.1, 16000))
+        files.append(str(p))
+    s = input_data.standard_microspeech_model_settings(3)
+    a = input_data.AudioDataset(s, ["hola"], str(bgd), files[3:], unknown_percentage=40.0, silence_percentage=20.0, seed=5)
+    b = input_data.AudioDataset(s, ["hola"], str(bgd), files[3:], unknown_percentage=40.0, silence_percentage=20.0, seed=5,
+                                device_augment=True)
+    monkeypatch.setattr(b, "_bank_row", lambda f: files.index(os.fspath(f)))
+    modes = set()
+    for k in range(200):
+        f = files[k % 3]
+        _, la = a.augment(a.decode_audio(f), "hola")
+        item, lb = b.augment_plan(files.index(f), "hola")
+        assert la == lb
+        assert a.gen.bit_generator.state == b.gen.bit_generator.state
+        modes.add(int(item["mode"]))
+        if lb == input_data.UNKNOWN_WORD_LABEL:
+            assert int(item["fg_index"]) >= 3
+    assert modes == {0, 1, 2}
