@@ -77,31 +77,45 @@ __device__ __forceinline__ void load_tables(FrontendTables* dst_smem, const Fron
 }
 
 // ---------------------------------------------------------------- fused clip kernel
-__global__ void __launch_bounds__(kClipThreads)
+__global__ void __launch_bounds__(kClipThreads, 5)   // <= 96 registers: five CTAs per SM (shared memory allows five)
 frontend_clip_kernel(const int16_t* __restrict__ pcm, int n_samples, int n_frames, int num_channels,
                      const FrontendTables* __restrict__ tables, float out_scale, float* __restrict__ out_f32,
-                     uint16_t* __restrict__ out_u16, int stage_bytes, int region_bytes, int use_tma) {
+                     uint16_t* __restrict__ out_u16, int stage_bytes, int region_bytes, int use_tma, int slot_bytes,
+                     int T_step, int window) {
   extern __shared__ __align__(128) uint8_t smem[];
   FrontendTables& T = *reinterpret_cast<FrontendTables*>(smem);
   uint8_t* p = smem + sizeof(FrontendTables);
   int16_t* s_pcm = reinterpret_cast<int16_t*>(p);            p += region_bytes;
   FrameScratch* scratch = reinterpret_cast<FrameScratch*>(p); p += sizeof(FrameScratch) * kHalfWarpsPerCta;
   uint32_t* s_mags = reinterpret_cast<uint32_t*>(p);          p += ((n_frames * num_channels * 4 + 15) & ~15);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(p);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(p);      // two barriers (ring slots)
 
   const int tid = threadIdx.x;
   const int clip = blockIdx.x;
   const int16_t* clip_pcm = pcm + (size_t)clip * n_samples;
 
+  // PCM staging.  TMA path: a two-slot ring — round r (8 frames = 7 steps + one window of samples, 5 440 B for the
+  // reference's 30 ms / 20 ms framing) is bulk-copied into slot r & 1 two rounds ahead of its use, so the CTA holds
+  // 11 KB of PCM instead of the whole 32 KB clip and five CTAs (20 warps) share an SM instead of three.
+  const int step = T_step;
+  const int rounds = (n_frames + kHalfWarpsPerCta - 1) / kHalfWarpsPerCta;
+  const int slot_samples = slot_bytes / 2;
+  auto issue_round = [&](int r) {                      // one thread
+    const int first = r * kHalfWarpsPerCta, last = min(first + kHalfWarpsPerCta, n_frames) - 1;
+    const uint32_t bytes = (uint32_t)((((last - first) * step + window) * 2 + 15) & ~15);
+    mbar_expect_tx(bar + (r & 1), bytes);
+    tma_bulk_g2s(s_pcm + (r & 1) * slot_samples, clip_pcm + (size_t)first * step, bytes, bar + (r & 1));
+  };
   if (use_tma) {
     if (tid == 0) {
       ptx::mbar_init(bar, 1);
+      ptx::mbar_init(bar + 1, 1);
       ptx::fence_barrier_init();
     }
     __syncthreads();
     if (tid == 0) {
-      mbar_expect_tx(bar, (uint32_t)stage_bytes);
-      tma_bulk_g2s(s_pcm, clip_pcm, (uint32_t)stage_bytes, bar);
+      issue_round(0);
+      if (rounds > 1) issue_round(1);
     }
   } else {
     const int n = stage_bytes / 2;
@@ -113,16 +127,21 @@ frontend_clip_kernel(const int16_t* __restrict__ pcm, int n_samples, int n_frame
   uint32_t tw2[15];
   fe_load_tw2(lane, tables->twiddles, tw2);
   __syncthreads();
-  if (use_tma) mbar_wait(bar, 0);
 
   // Phase A: frames -> magnitudes (half-warp per frame)
-  const int step = T.window_step;
-  for (int base = 0; base < n_frames; base += kHalfWarpsPerCta) {
+  for (int r = 0; r < rounds; ++r) {
+    const int base = r * kHalfWarpsPerCta;
     const int f = base + hw;
     const bool valid = f < n_frames;
-    const int ff = valid ? f : 0;
-    halfwarp_frame_mags(reinterpret_cast<const uint32_t*>(s_pcm + ff * step), T, tw2, scratch[hw], lane,
+    const int ff = valid ? f : base;
+    const int16_t* frame = use_tma ? s_pcm + (r & 1) * slot_samples + (ff - base) * step : s_pcm + ff * step;
+    if (use_tma) mbar_wait(bar + (r & 1), (uint32_t)(r >> 1) & 1u);
+    halfwarp_frame_mags(reinterpret_cast<const uint32_t*>(frame), T, tw2, scratch[hw], lane,
                         s_mags + ff * num_channels, valid);
+    if (use_tma && r + 2 < rounds) {
+      __syncthreads();                                 // every half-warp has left slot r & 1
+      if (tid == 0) issue_round(r + 2);
+    }
   }
   __syncthreads();
 
@@ -362,13 +381,18 @@ extern "C" int kws_frontend_forward(kws_frontend_t* fe, const int16_t* d_pcm, in
   const int needed = (n_frames - 1) * T.window_step + T.window_size;       // samples actually consumed
   const bool tma_ok = ((size_t)n_samples * 2 % 16 == 0) && (((uintptr_t)d_pcm & 15) == 0);
   const int stage_bytes = (int)round_up((size_t)needed * 2, 16);
-  const int region_bytes = (int)round_up(stage_bytes > n_frames * C * 4 ? stage_bytes : n_frames * C * 4, 16);
+  // TMA path: two ring slots of one 8-frame round each; fallback (unaligned PCM): the whole clip.  The region is
+  // reused for the noise estimates after the magnitudes are done, so it is at least n_frames * C words.
+  const int slot_bytes = (int)round_up((size_t)((kHalfWarpsPerCta - 1) * T.window_step + T.window_size) * 2, 16);
+  const int pcm_bytes = tma_ok ? 2 * slot_bytes : stage_bytes;
+  const int region_bytes = (int)round_up(pcm_bytes > n_frames * C * 4 ? pcm_bytes : n_frames * C * 4, 16);
   const size_t smem = sizeof(FrontendTables) + region_bytes + sizeof(FrameScratch) * kHalfWarpsPerCta +
-                      round_up((size_t)n_frames * C * 4, 16) + 16;
+                      round_up((size_t)n_frames * C * 4, 16) + 32;
   if (smem <= (size_t)fe->max_smem_optin) {
     KWS_CUDA_CHECK(cudaFuncSetAttribute(frontend_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     frontend_clip_kernel<<<batch, kClipThreads, smem, st>>>(d_pcm, n_samples, n_frames, C, fe->dev, out_scale, d_out_f32,
-                                                          d_out_u16, stage_bytes, region_bytes, tma_ok ? 1 : 0);
+                                                          d_out_u16, stage_bytes, region_bytes, tma_ok ? 1 : 0, slot_bytes,
+                                                          T.window_step, T.window_size);
     KWS_CUDA_CHECK(cudaGetLastError());
     return KWS_OK;
   }
