@@ -252,8 +252,9 @@ __device__ __forceinline__ void se_narrow(float* s_pool, float* s_se, const floa
   __syncthreads();
 }
 
+// block1a (GEOM 7: 64 KB of tiles per clip, 3x3 taps) fits three CTAs per SM in shared memory; its register cap follows
 template <int K, int S, int GEOM>
-__global__ void __launch_bounds__(kDwThreads, 2)     // <= 128 registers: two CTAs per SM wherever shared memory allows
+__global__ void __launch_bounds__(kDwThreads, GEOM == 7 ? 3 : 2)     // <= 128 (80) registers: two (three) CTAs per SM
 dwse_kernel(const uint16_t* __restrict__ x, int batch, int G, DwseParams P, uint16_t* __restrict__ y) {
   extern __shared__ __align__(128) uint8_t smem[];
   const DwSmem L = dw_smem(P, G);
@@ -644,7 +645,7 @@ int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int 
   else if (is(5, 1, 7, 5, 2, 2) && P.C == 240) kern = dwse_kernel<5, 1, 11>;
   KWS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_groups = (batch + G - 1) / G;
-  const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+  const int per_sm = (kern == dwse_kernel<3, 1, 7> && smem <= 74 * 1024) ? 3 : (smem <= 100 * 1024 ? 2 : 1);
   KWS_REQUIRE(smem <= (size_t)kDwSmemCap, "dwse: %zu bytes of shared memory exceed the per-CTA limit", smem);
   const int grid = n_groups < sm_count * per_sm ? n_groups : sm_count * per_sm;
   KWS_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kDwThreads), smem, st, static_cast<const uint16_t*>(d_x), batch, G, P,
