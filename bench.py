@@ -252,13 +252,16 @@ def run_ours(args, rank, local_rank, world):
     ov_bufs = [(torch.empty_like(feats), torch.empty_like(emb),
                 torch.empty(emb_model.workspace_bytes(B), dtype=torch.uint8, device=dev)) for _ in range(n_str)]
 
+    from multilingual_kws_b200.pipeline import EmbedPipeline
+    ov_budget = EmbedPipeline.SM_BUDGET if n_str > 1 else None        # the schedule the host pipeline uses
+
     def ov_step(k):
         f, o, w_ = ov_bufs[k % n_str]
         st = ov_streams[k % n_str]
         st.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(st):
             fe.forward(pcm, out=f)
-            emb_model.forward_device(f, out=o, workspace=w_)
+            emb_model.forward_device(f, out=o, workspace=w_, sm_budget=ov_budget)
 
     def ov_join():
         for st in ov_streams:

@@ -106,6 +106,11 @@ size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch);
 /* d_feats fp32 [batch, 49, 40] (the frontend's output) -> d_emb fp32 [batch, out_dim] */
 int kws_embed_forward(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
                       size_t ws_bytes, void* stream);
+/* Throughput schedule for callers that keep several forward passes in flight on different streams: the grids of the
+ * network's head (stem ... block3b) are sized for sm_head SMs, those of its launch/latency-bound tail for sm_tail SMs
+ * (0 = all SMs), so the tail's persistent CTAs leave room for a neighbouring pass.  Same results as kws_embed_forward. */
+int kws_embed_forward_budget(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
+                             size_t ws_bytes, int sm_head, int sm_tail, void* stream);
 /* same, additionally copying the output of op `tap_op` (bf16 NHWC; fp32 for the last op) to d_tap */
 int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
                           size_t ws_bytes, int tap_op, void* d_tap, void* stream);

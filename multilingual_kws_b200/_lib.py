@@ -43,6 +43,7 @@ SIGNATURES = {
     "kws_embed_set_chunk": (c_int, [c_void_p, c_int]),
     "kws_embed_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "kws_embed_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kws_embed_forward_budget": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "kws_embed_forward_tap": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
     "kws_gemm_h16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                              c_int, c_int, c_void_p]),

@@ -100,7 +100,7 @@ struct Op {
 }  // namespace
 
 struct GraphEntry {
-  const float* feats; float* emb; void* ws; int batch, chunk;
+  const float* feats; float* emb; void* ws; int batch; long long chunk;   // chunk: schedule key (chunks + SM budgets)
   cudaGraphExec_t exec;
 };
 
@@ -119,6 +119,10 @@ struct kws_embed {
   size_t max_se_channels = 0;          // widest externally-gated layer (scratch: pooled means, squeeze, gates)
   size_t buf_elems[2][3] = {{0, 0, 0}, {0, 0, 0}};   // [segment][X, E, D] per clip, 16-bit elements
   int sm_count = 0, max_smem = 0;
+  // Throughput schedule (kws_embed_forward_budget): when several forward passes are in flight on different streams, the
+  // launch/latency-bound tail of the network (everything after block3b: maps of <= 4x3 pixels) is sized for a subset
+  // of the SMs, so its persistent CTAs leave room for the throughput-bound head of the neighbouring pass.
+  int tail_op = 0;                     // first op of the tail
   int chunk = 1024;                    // early-segment clips per pass
   int chunk_late = 4096;               // late-segment clips per pass
   int se_via_gemm = 1;                 // wide layers: SE FCs as batched tcgen05 GEMMs (0: inside the depthwise kernel)
@@ -485,6 +489,9 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
     delete m;
     return KWS_ERR_UNSUPPORTED;
   }
+  m->tail_op = m->split_op;
+  for (size_t i = 0; i < m->ops.size(); ++i)
+    if (m->ops[i].name == "block3b_out") m->tail_op = (int)i + 1;
   m->flops_per_clip = 2.0 * macs;
   *out = m;
   return KWS_OK;
@@ -575,12 +582,13 @@ extern "C" size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch) {
 
 // tap_op >= 0: additionally copy the output of op `tap_op` (bf16 NHWC, or fp32 for the last op) to d_tap.
 static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace, int tap_op,
-                   void* d_tap, float* host_op_ms, cudaStream_t st);
+                   void* d_tap, float* host_op_ms, cudaStream_t st, int sm_head, int sm_tail);
 
 // The launch list of one forward pass is fixed for given buffers / batch, so it is captured once into a CUDA
 // graph (35 tensor-map encodes + ~55 launches per chunk collapse into one cudaGraphLaunch) and replayed.
 static int embed_forward_impl(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
-                              size_t ws_bytes, int tap_op, void* d_tap, float* host_op_ms, void* stream) {
+                              size_t ws_bytes, int tap_op, void* d_tap, float* host_op_ms, void* stream, int sm_head = 0,
+                              int sm_tail = 0) {
   KWS_REQUIRE(m != nullptr, "kws_embed_forward: NULL handle");
   KWS_REQUIRE(batch >= 0, "kws_embed_forward: negative batch");
   if (batch == 0) return KWS_OK;
@@ -591,15 +599,15 @@ static int embed_forward_impl(kws_embed_t* m, const float* d_feats, int batch, f
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (m->use_graph && tap_op < 0 && !host_op_ms && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
       cap == cudaStreamCaptureStatusNone) {
+    const long long sched_key = (((long long)m->chunk * 100003 + m->chunk_late) * 1024 + sm_head) * 1024 + sm_tail;
     for (auto& g : m->graphs)
-      if (g.feats == d_feats && g.emb == d_emb && g.ws == d_workspace && g.batch == batch &&
-          g.chunk == m->chunk * 100003 + m->chunk_late) {
+      if (g.feats == d_feats && g.emb == d_emb && g.ws == d_workspace && g.batch == batch && g.chunk == sched_key) {
         KWS_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
         return KWS_OK;
       }
     if (!m->cap_stream) KWS_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
     KWS_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = run_ops(m, d_feats, batch, d_emb, d_workspace, -1, nullptr, nullptr, m->cap_stream);
+    const int rc = run_ops(m, d_feats, batch, d_emb, d_workspace, -1, nullptr, nullptr, m->cap_stream, sm_head, sm_tail);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &graph);
     if (rc != KWS_OK) {
@@ -607,7 +615,7 @@ static int embed_forward_impl(kws_embed_t* m, const float* d_feats, int batch, f
       return rc;
     }
     KWS_CUDA_CHECK(ce);
-    GraphEntry e{d_feats, d_emb, d_workspace, batch, m->chunk * 100003 + m->chunk_late, nullptr};
+    GraphEntry e{d_feats, d_emb, d_workspace, batch, sched_key, nullptr};
     const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
     cudaGraphDestroy(graph);
     KWS_CUDA_CHECK(ie);
@@ -619,11 +627,13 @@ static int embed_forward_impl(kws_embed_t* m, const float* d_feats, int batch, f
     KWS_CUDA_CHECK(cudaGraphLaunch(e.exec, st));
     return KWS_OK;
   }
-  return run_ops(m, d_feats, batch, d_emb, d_workspace, tap_op, d_tap, host_op_ms, st);
+  return run_ops(m, d_feats, batch, d_emb, d_workspace, tap_op, d_tap, host_op_ms, st, sm_head, sm_tail);
 }
 
 static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace, int tap_op,
-                   void* d_tap, float* host_op_ms, cudaStream_t st) {
+                   void* d_tap, float* host_op_ms, cudaStream_t st, int sm_head, int sm_tail) {
+  const int sms_head = (sm_head > 0 && sm_head < m->sm_count) ? sm_head : m->sm_count;
+  const int sms_tail = (sm_tail > 0 && sm_tail < m->sm_count) ? sm_tail : m->sm_count;
   const int n_ops = (int)m->ops.size();
   const int chunk_seg[2] = {batch < m->chunk ? batch : m->chunk, batch < m->chunk_late ? batch : m->chunk_late};
   // workspace carve-up: [Xe | Ee | De] (early chunk) [H = late X, whole batch] [El | Dl] (late chunk)
@@ -667,29 +677,30 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
       if (host_op_ms) { KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st)); ev_op.push_back(-1); }
       for (int oi = op_lo; oi < op_hi; ++oi) {
         const Op& op = m->ops[oi];
+        const int sms = oi >= m->tail_op ? sms_tail : sms_head;
         void* out_ptr = op.out_buf >= 0 ? (void*)bufs[op.out_buf] : (void*)(d_emb + (size_t)b0 * m->out_dim);
         if (sgi == 0 && oi == m->split_op - 1 && op.out_buf == 0)      // hand-off: early chunk -> late X (whole batch)
           out_ptr = H + m->buf_elems[1][0] * (size_t)b0;
         int rc = KWS_OK;
         if (op.kind == kOpStem) {
-          rc = launch_stem(d_feats + (size_t)b0 * m->H * m->W, nb, op.stem, out_ptr, m->sm_count, st);
+          rc = launch_stem(d_feats + (size_t)b0 * m->H * m->W, nb, op.stem, out_ptr, sms, st);
         } else if (op.kind == kOpDwse) {
           DwseParams P = op.dw;
           P.pooled_out = se_pooled;
-          rc = launch_dwse(bufs[op.in_buf], nb, P, out_ptr, dwse_pick_group(P, m->max_smem, nb, m->sm_count), m->sm_count, st);
+          rc = launch_dwse(bufs[op.in_buf], nb, P, out_ptr, dwse_pick_group(P, m->max_smem, nb, sms), sms, st);
           if (rc == KWS_OK && P.se_external) {
             GemmEpilogue e1;
             e1.bias = op.se_b1; e1.residual = nullptr; e1.out = se_squeeze; e1.ldo = op.se_pad; e1.ldr = op.se_pad;
             e1.act = kActSwish; e1.out_f32 = 0; e1.gap4 = 0; e1.bf16 = m->bf16;
-            rc = gemm_h16(se_pooled, op.se_w1, nb, op.se_pad, P.C, 0, e1, m->sm_count, st);
+            rc = gemm_h16(se_pooled, op.se_w1, nb, op.se_pad, P.C, 0, e1, sms, st);
             if (rc == KWS_OK) {
               GemmEpilogue e2 = e1;
               // (applying the gates inside this epilogue measured slower than the separate coalesced gating pass:
               //  one thread per clip would walk the pixels with a 2*C-byte stride)
               e2.bias = P.b_se2; e2.out = se_gates; e2.ldo = P.C; e2.ldr = P.C; e2.act = kActSigmoid;
-              rc = gemm_h16(se_squeeze, op.se_w2, nb, P.C, op.se_pad, 0, e2, m->sm_count, st);
+              rc = gemm_h16(se_squeeze, op.se_w2, nb, P.C, op.se_pad, 0, e2, sms, st);
             }
-            if (rc == KWS_OK) rc = launch_se_scale(out_ptr, se_gates, nb, P.Ho * P.Wo, P.C, m->bf16, m->sm_count, st);
+            if (rc == KWS_OK) rc = launch_se_scale(out_ptr, se_gates, nb, P.Ho * P.Wo, P.C, m->bf16, sms, st);
           }
         } else {
           GemmEpilogue ep;
@@ -697,7 +708,7 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
           ep.residual = op.res_buf >= 0 ? bufs[op.res_buf] : nullptr;
           ep.out = out_ptr; ep.ldo = op.N; ep.ldr = op.N;
           ep.act = op.act; ep.out_f32 = op.out_f32; ep.gap4 = op.gap4; ep.bf16 = m->bf16;
-          rc = gemm_h16(bufs[op.in_buf], op.w, op.rows_per_clip * nb, op.N, op.K, 0, ep, m->sm_count, st);
+          rc = gemm_h16(bufs[op.in_buf], op.w, op.rows_per_clip * nb, op.N, op.K, 0, ep, sms, st);
         }
         if (rc != KWS_OK) return rc;
         if (host_op_ms) { KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st)); ev_op.push_back(oi); }
@@ -730,6 +741,16 @@ extern "C" int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int b
 extern "C" int kws_embed_forward(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
                                  size_t ws_bytes, void* stream) {
   return embed_forward_impl(m, d_feats, batch, d_emb, d_workspace, ws_bytes, -1, nullptr, nullptr, stream);
+}
+
+// Throughput schedule: as kws_embed_forward, with the grids of the network's head (stem ... block3b) sized for sm_head
+// SMs and those of its latency-bound tail for sm_tail SMs (0 = all).  Meant for callers that keep several forward
+// passes in flight on different streams (EmbedPipeline): results are identical, a single pass gets slower, the
+// overlapped throughput higher (profiles/README.md item 11).
+extern "C" int kws_embed_forward_budget(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
+                                        size_t ws_bytes, int sm_head, int sm_tail, void* stream) {
+  KWS_REQUIRE(sm_head >= 0 && sm_tail >= 0 && sm_head < 1024 && sm_tail < 1024, "kws_embed_forward_budget: bad SM budget");
+  return embed_forward_impl(m, d_feats, batch, d_emb, d_workspace, ws_bytes, -1, nullptr, nullptr, stream, sm_head, sm_tail);
 }
 
 // Profiling variant: CUDA events around every op on `stream`; host_op_ms[n_ops] receives the per-op device time

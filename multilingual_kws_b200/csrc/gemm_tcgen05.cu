@@ -28,12 +28,17 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5: one MUFU op instead of EX2 + RCP (the result is rounded to 16 bits anyway)
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == kActSwish) { const float h = 0.5f * x; return fmaf(h, tanh_approx(h), h); }
+// sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5: one MUFU op instead of EX2 + RCP (the result is rounded to 16 bits anyway).
+// swish / sigmoid need h = 0.5 (acc + bias): the bias vector is stored pre-halved in shared memory for these two
+// activations, so h is ONE fma(acc, 0.5, bias/2) per element — bit-identical to 0.5f * (acc + bias) (scaling by a power
+// of two is exact) and one instruction less.
+__device__ __forceinline__ bool act_halves_bias(int act) { return act == kActSwish || act == kActSigmoid; }
+__device__ __forceinline__ float bias_act(float acc, float b, int act) {      // b = bias, or bias / 2 (see above)
+  if (act == kActSwish) { const float h = fmaf(acc, 0.5f, b); return fmaf(h, tanh_approx(h), h); }
+  if (act == kActSigmoid) return fmaf(0.5f, tanh_approx(fmaf(acc, 0.5f, b)), 0.5f);
+  const float x = acc + b;
   if (act == kActRelu) return fmaxf(x, 0.0f);
   if (act == kActSelu) return x > 0.0f ? 1.0507009873554805f * x : 1.7580993408473766f * (__expf(x) - 1.0f);
-  if (act == kActSigmoid) return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f);
   return x;
 }
 
@@ -70,11 +75,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmShape& sh, const GemmEp
       float4 b;
       asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                    : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(s_bias_addr + (uint32_t)(n0 + 4 * q) * 4u));
-      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+      v[4 * q] = bias_act(v[4 * q], b.x, act); v[4 * q + 1] = bias_act(v[4 * q + 1], b.y, act);
+      v[4 * q + 2] = bias_act(v[4 * q + 2], b.z, act); v[4 * q + 3] = bias_act(v[4 * q + 3], b.w, act);
     }
   }
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], act);
   // residual and 16-bit output rows are 32-byte aligned when the row pitch is a multiple of 16 elements
   if (has_res && row_ok) {          // plain (coherent) loads: the residual may alias the output (in-place skip); each
     uint32_t w[8];                  // thread reads exactly the bytes it overwrites below
@@ -143,7 +147,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_bias = reinterpret_cast<float*>(smem + L.bias_off);
   // the bias vector (a constant of the layer: safe to read before the dependency wait below) goes to smem once
-  for (int i = threadIdx.x; i < ((sh.N + 15) & ~15); i += kGemmThreads) s_bias[i] = (ep.bias && i < sh.N) ? __ldg(ep.bias + i) : 0.0f;
+  {
+    const float bscale = act_halves_bias(ACT >= 0 ? ACT : ep.act) ? 0.5f : 1.0f;
+    for (int i = threadIdx.x; i < ((sh.N + 15) & ~15); i += kGemmThreads)
+      s_bias[i] = (ep.bias && i < sh.N) ? bscale * __ldg(ep.bias + i) : 0.0f;
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int block_n = sh.block_n, stages = sh.stages;

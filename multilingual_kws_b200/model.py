@@ -153,11 +153,12 @@ class EmbeddingModel:
         return int(_lib.lib().kws_embed_workspace_bytes(self._h, int(batch)))
 
     def forward_device(self, feats: torch.Tensor, out: Optional[torch.Tensor] = None, tap_op: int = -1,
-                       workspace: Optional[torch.Tensor] = None):
+                       workspace: Optional[torch.Tensor] = None, sm_budget: Optional[tuple] = None):
         """feats: CUDA float32 [B,49,40] (contiguous) -> CUDA float32 [B, output_dim].  With tap_op >= 0 also
         returns that op's output (bf16 [B, elems], fp32 for the last op).  `workspace` (uint8 CUDA tensor of at least
         workspace_bytes(B)) replaces the model's own scratch: forwards that run concurrently on different streams
-        must not share one."""
+        must not share one.  `sm_budget` = (head SMs, tail SMs) selects the throughput schedule
+        (kws_embed_forward_budget) for callers that overlap several passes; results are identical."""
         if feats.dim() == 4 and feats.shape[-1] == 1:
             feats = feats[..., 0]
         if feats.dim() != 3 or tuple(feats.shape[1:]) != self.input_hw:
@@ -177,7 +178,11 @@ class EmbeddingModel:
             tap = torch.empty((B, elems), dtype=torch.float32 if last else (torch.float16 if self.dtype == "fp16" else torch.bfloat16),
                               device=self.device)
             tap_ptr = tap.data_ptr()
-        if B:
+        if B and sm_budget is not None and tap_op < 0:
+            _lib.check(_lib.lib().kws_embed_forward_budget(self._h, feats.data_ptr(), B, out.data_ptr(), ws.data_ptr(),
+                                                           ws.numel(), int(sm_budget[0]), int(sm_budget[1]),
+                                                           _lib.current_stream_ptr()), "kws_embed_forward_budget")
+        elif B:
             _lib.check(_lib.lib().kws_embed_forward_tap(self._h, feats.data_ptr(), B, out.data_ptr(), ws.data_ptr(),
                                                         ws.numel(), int(tap_op), tap_ptr, _lib.current_stream_ptr()),
                        "kws_embed_forward")

@@ -32,8 +32,13 @@ from .model import EmbeddingModel
 
 
 class EmbedPipeline:
+    # (head SMs, tail SMs) of the throughput schedule when several compute streams overlap (0 = all): the tail of the
+    # network (after block3b) is launch/latency-bound and sized for 80 of the 148 SMs so that it leaves room for the
+    # throughput-bound head of the neighbouring job (measured: profiles/README.md item 11)
+    SM_BUDGET = (132, 80)
+
     def __init__(self, frontend: MicroFrontend, model: EmbeddingModel, n_samples: int = 16000, sub_batch: int = 512,
-                 depth: int = 4, streams: int = 2):
+                 depth: int = 4, streams: int = 2, sm_budget: Optional[tuple] = None):
         if depth < 2 or streams < 1 or depth % streams:
             raise ValueError("EmbedPipeline needs at least two device slots, depth a multiple of streams")
         self.fe, self.model, self.n, self.sub, self.depth = frontend, model, int(n_samples), int(sub_batch), int(depth)
@@ -51,6 +56,7 @@ class EmbedPipeline:
         self._ran = [torch.cuda.Event() for _ in range(depth)]
         self._downloaded = [torch.cuda.Event() for _ in range(depth)]
         self._jobs = 0                      # jobs enqueued since construction (slot = job % depth)
+        self.sm_budget = sm_budget if sm_budget is not None else (self.SM_BUDGET if int(streams) > 1 else None)
 
     def alloc_input(self, batch: int) -> torch.Tensor:
         """int16 [batch, n_samples] upload buffer in write-combined pinned memory (fill it with PCM, do not read it
@@ -89,7 +95,8 @@ class EmbedPipeline:
                 compute.wait_event(self._downloaded[s])
             with torch.cuda.stream(compute):
                 self.fe.forward(self._pcm[s][:nb], out_scale=FEATURE_SCALE, out=self._feat[s][:nb])
-                self.model.forward_device(self._feat[s][:nb], out=self._emb[s][:nb], workspace=self._ws[s])
+                self.model.forward_device(self._feat[s][:nb], out=self._emb[s][:nb], workspace=self._ws[s],
+                                          sm_budget=self.sm_budget)
                 self._ran[s].record(compute)
             with torch.cuda.stream(self._down):
                 self._down.wait_event(self._ran[s])

@@ -112,3 +112,12 @@ def test_monolingual_head_sizes(kws_lib, feats):
     got = EmbeddingModel(w).predict(feats[:16])
     want = EO.forward(w, feats[:16]).numpy()
     assert got.shape == (16, 192) and EO.cosine(got, want).min() >= 0.999
+
+
+def test_throughput_schedule_same_results(setup, feats):
+    """kws_embed_forward_budget (tail of the network sized for a subset of the SMs): identical embeddings."""
+    model = setup[0]
+    x = torch.from_numpy(np.tile(feats, (8, 1, 1))).cuda()
+    want = model.forward_device(x).clone()
+    for budget in ((132, 80), (0, 32), (64, 0), (148, 148)):
+        assert torch.equal(model.forward_device(x, sm_budget=budget), want), budget
