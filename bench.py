@@ -254,6 +254,8 @@ def run_ours(args, rank, local_rank, world):
 
     from multilingual_kws_b200.pipeline import EmbedPipeline
     ov_budget = EmbedPipeline.SM_BUDGET if n_str > 1 else None        # the schedule the host pipeline uses
+    if args.sm_budget:
+        ov_budget = tuple(int(x) for x in args.sm_budget.split(","))
 
     def ov_step(k):
         f, o, w_ = ov_bufs[k % n_str]
@@ -289,7 +291,8 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- e2e: public API, host buffers (pinned), H2D + D2H inside the timed region
     from multilingual_kws_b200.pipeline import EmbedPipeline
-    pipe = EmbedPipeline(fe, emb_model, n_samples=16000, sub_batch=B, depth=2 * args.pipe_streams, streams=args.pipe_streams)
+    pipe = EmbedPipeline(fe, emb_model, n_samples=16000, sub_batch=B, depth=2 * args.pipe_streams, streams=args.pipe_streams,
+                         sm_budget=ov_budget)
     # host buffers: two input sets in write-combined pinned memory (kws_host_alloc), two pinned result buffers
     pcm_pinned2 = [pipe.alloc_input(B), pipe.alloc_input(B)]
     pcm_pinned2[0].copy_(torch.from_numpy(pcm_host))
@@ -494,6 +497,7 @@ def main():
                     help="wall-clock budget of the whole --impl reference run (the per-step sample is sized to fit)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipe-streams", type=int, default=3, help="compute streams the host pipeline / overlapped figure rotate over")
+    ap.add_argument("--sm-budget", default="", help="head,tail SM budget of the throughput schedule (default: the pipeline's)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying the CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -33,9 +33,9 @@ from .model import EmbeddingModel
 
 class EmbedPipeline:
     # (head SMs, tail SMs) of the throughput schedule when several compute streams overlap (0 = all): the tail of the
-    # network (after block3b) is launch/latency-bound and sized for 80 of the 148 SMs so that it leaves room for the
+    # network (after block3b) is launch/latency-bound and sized for 72 of the 148 SMs so that it leaves room for the
     # throughput-bound head of the neighbouring job (measured: profiles/README.md item 11)
-    SM_BUDGET = (132, 80)
+    SM_BUDGET = (132, 72)
 
     def __init__(self, frontend: MicroFrontend, model: EmbeddingModel, n_samples: int = 16000, sub_batch: int = 512,
                  depth: int = 4, streams: int = 2, sm_budget: Optional[tuple] = None):
