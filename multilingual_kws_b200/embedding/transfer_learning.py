@@ -55,6 +55,48 @@ def train_step(model: FewShotModel, specs: torch.Tensor, labels: torch.Tensor, l
     return stats[0] / cnt, stats[1] / cnt
 
 
+def train_steps_grouped(model: FewShotModel, batches, lr: float):
+    """`len(batches)` consecutive optimisation steps with ONE embedding forward.
+
+    The embedding is frozen while the head trains (reference transfer_learning.py:43 `embedding.trainable = False`), so
+    its outputs do not depend on the head's updates: the spectrograms of G consecutive steps go through the tower as one
+    batch of G x batch_size clips (where the kernels are throughput- instead of launch-bound), then the G head steps
+    (forward + loss + backward, all-reduce under torch.distributed, Adam) run in order on their slices.  Per-clip
+    embeddings do not depend on how clips are batched, so every step computes exactly what `train_step` computes.
+    batches: list of (specs [n,49,40(,1)] CUDA, labels [n] CUDA int); returns [(mean loss, accuracy)] per step, read
+    from the device once for the whole group."""
+    dist = _dist()
+    shards = []
+    for specs, labels in batches:
+        if dist is not None:
+            r, ws = dist.get_rank(), dist.get_world_size()
+            n = specs.shape[0]
+            lo, hi = n * r // ws, n * (r + 1) // ws
+            specs, labels = specs[lo:hi], labels[lo:hi]
+        shards.append((specs[..., 0] if specs.dim() == 4 else specs, labels))
+    sizes = [s.shape[0] for s, _ in shards]
+    emb_all = model.embedding.forward_device(torch.cat([s for s, _ in shards])) if sum(sizes) else None
+    flat = model.head._flat
+    n_p = model.head.n_params
+    stats = torch.empty((len(shards), 3), dtype=torch.float32, device=flat.device)
+    off = 0
+    for i, ((_, labels), n) in enumerate(zip(shards, sizes)):
+        if n > 0:
+            model.head.grad(emb_all[off:off + n], labels, out=flat)
+        else:
+            flat.zero_()
+        off += n
+        if dist is not None:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        stats[i].copy_(flat[n_p:n_p + 3])
+        model.head.apply_adam(flat, lr)
+    out = []
+    for loss_sum, correct, cnt in stats.tolist():
+        cnt = max(cnt, 1.0)
+        out.append((loss_sum / cnt, correct / cnt))
+    return out
+
+
 def evaluate(model: FewShotModel, ds) -> Dict[str, float]:
     """Loss / accuracy over a (batched) dataset, forward only."""
     loss_sum, correct, n = 0.0, 0, 0
@@ -69,7 +111,9 @@ def evaluate(model: FewShotModel, ds) -> Dict[str, float]:
 
 
 def fit(model: FewShotModel, train_ds, validation_data, steps_per_epoch: int, epochs: int, lr: float,
-        csvlog_dest=None, verbose=1) -> Dict[str, List[float]]:
+        csvlog_dest=None, verbose=1, group_clips: int = 2048) -> Dict[str, List[float]]:
+    """Keras-style fit of the head.  Steps are executed in groups that share one embedding forward of about
+    `group_clips` clips (`train_steps_grouped`; group_clips = 0: one forward per step) — same updates, same history."""
     history = {"loss": [], "accuracy": [], "val_loss": [], "val_accuracy": []}
     it = iter(train_ds)
     writer = None
@@ -80,11 +124,18 @@ def fit(model: FewShotModel, train_ds, validation_data, steps_per_epoch: int, ep
         writer.writerow(["epoch", "accuracy", "loss", "val_accuracy", "val_loss"])   # Keras CSVLogger column order
     for epoch in range(epochs):
         loss_sum, acc_sum = 0.0, 0.0
-        for _ in range(steps_per_epoch):
+        done = 0
+        while done < steps_per_epoch:
             specs, labels = next(it)
-            loss, acc = train_step(model, specs.cuda(), labels.cuda(), lr)
-            loss_sum += loss
-            acc_sum += acc
+            group = [(specs.cuda(), labels.cuda())]
+            want = max(1, group_clips // max(int(specs.shape[0]), 1)) if group_clips > 0 else 1
+            while len(group) < min(want, steps_per_epoch - done):
+                specs, labels = next(it)
+                group.append((specs.cuda(), labels.cuda()))
+            for loss, acc in train_steps_grouped(model, group, lr):
+                loss_sum += loss
+                acc_sum += acc
+            done += len(group)
         val = evaluate(model, validation_data)
         history["loss"].append(loss_sum / steps_per_epoch)
         history["accuracy"].append(acc_sum / steps_per_epoch)

@@ -213,3 +213,24 @@ def test_host_pipeline_back_to_back_calls(world):
         assert torch.equal(outs[0], want[0]) and torch.equal(outs[1], want[1])
     with pytest.raises(ValueError):
         pipe.run_host(torch.zeros((2, 100), dtype=torch.int16).pin_memory())
+
+
+def test_grouped_steps_equal_single_steps(world):
+    """train_steps_grouped (one embedding forward for G steps; the embedding is frozen) == G x train_step, bit for bit."""
+    from multilingual_kws_b200.embedding.transfer_learning import train_step, train_steps_grouped
+    from multilingual_kws_b200.fewshot import FewShotModel, Head
+    from multilingual_kws_b200.model import EmbeddingModel
+    from oracle import head_oracle as HO
+    emb_model = EmbeddingModel({k: v for k, v in world["w"].items() if not k.startswith("dense_3")})
+    feats = torch.from_numpy(world["feats"]).cuda()
+    rng = np.random.default_rng(2)
+    batches = []
+    for n in (16, 16, 7, 16, 1, 16):
+        idx = torch.from_numpy(rng.integers(0, 40, n)).cuda()
+        batches.append((feats[idx][..., None], torch.from_numpy(rng.integers(0, 3, n)).cuda()))
+    a = FewShotModel(emb_model, Head.from_params(HO.init_head(7)))
+    b = FewShotModel(emb_model, Head.from_params(HO.init_head(7)))
+    want = [train_step(a, x[..., 0], y, 1e-2) for x, y in batches]
+    got = train_steps_grouped(b, batches[:4], 1e-2) + train_steps_grouped(b, batches[4:], 1e-2)
+    assert got == want
+    assert np.array_equal(a.head.get_params(), b.head.get_params())

@@ -104,6 +104,27 @@ res["cfg3_finetune_100_steps_batch512"] = {
     "note": "each step: embedding forward (frozen) + head fwd/bwd + Adam; train_step returns loss/accuracy to the host "
             "(one D2H sync per step, as Keras' fit loop does for its progress bar)"}
 
+# grouped: what fit() does — the embedding is frozen, G consecutive steps share one embedding forward
+from multilingual_kws_b200.embedding.transfer_learning import train_steps_grouped
+rows = []
+for bs, steps, G in ((512, 100, 4), (64, 256, 32)):            # config 3, and the reference's default run (run.py: 4 x 64 steps of 64)
+    f_ = fe.forward(pcm_batch(bs, 3))[..., None]
+    y_ = torch.from_numpy(np.random.default_rng(7).integers(0, 3, bs).astype(np.int32)).to(dev)
+    res_row = {"batch": bs, "steps": steps, "steps_per_embedding_forward": G}
+    for name, fn in (("single", lambda: [train_step(ft, f_[..., 0], y_, 1e-3) for _ in range(steps)]),
+                     ("grouped", lambda: [train_steps_grouped(ft, [(f_, y_)] * min(G, steps - k), 1e-3) for k in range(0, steps, G)])):
+        ft.head.reset_optimizer()
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        w_ = time.perf_counter() - t0
+        res_row[name + "_wall_s"] = round(w_, 4)
+        res_row[name + "_utt_per_s"] = round(steps * bs / w_)
+    rows.append(res_row)
+res["cfg3_finetune_grouped_vs_single"] = rows
+
 # ---- cfg5: streaming
 n = 30 * 60 * 16000
 audio = torch.from_numpy(synthetic_stream(n, cfg_id=5)).to(dev)
