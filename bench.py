@@ -448,7 +448,12 @@ def run_ours(args, rank, local_rank, world):
             f, ref_emb = cpu_run(nb)
             reps += 1
         dt = (time.perf_counter() - t0) / reps
+        # frontend alone: single-threaded (the TF op is single-threaded per call) and one clip per thread
+        t0 = time.perf_counter(); orc.features_u16(pcm_host[:64]); fe_1 = 64 / (time.perf_counter() - t0)
+        nfe = min(B, 512)
+        t0 = time.perf_counter(); orc.features_u16(pcm_host[:nfe], threads=cores); fe_n = nfe / (time.perf_counter() - t0)
         cpu = {"value": nb / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "frontend_only_clips_per_s": {"single_thread": round(fe_1, 1), "all_threads": round(fe_n, 1)},
                "sample": f"{reps} x {nb} synthetic clips (frontend C oracle on {cores} threads + torch-CPU fp32 network)"}
         # parity spot-check against the oracle (checker only): same architecture/kernels, BN statistics calibrated
         # by the oracle so activations have trained-like scale (the timed model uses un-calibrated random weights)

@@ -58,19 +58,6 @@ for B in (32, 1024, 8192, 32768):
     rows.append({"batch": B, "ms": round(ms, 4), "clips_per_s": round(B / ms * 1e3), "algorithmic_GBps": round(B * 39840 / ms / 1e6, 1)})
 res["cfg1_frontend_only"] = rows
 
-# CPU column for the frontend: the C oracle single-threaded (the TF op is single-threaded per call) and
-# one clip per thread over the usable host threads (what tf.data AUTOTUNE does, input_data.py:452-471)
-import bench as _bench
-from oracle.frontend_oracle import FrontendOracle
-_orc = FrontendOracle()
-_cpu_pcm = synthetic_pcm(256, cfg_id=1)
-_thr = _bench.host_threads()
-t0 = time.perf_counter(); _orc.features_u16(_cpu_pcm[:64]); t1 = time.perf_counter() - t0
-_orc.features_u16(_cpu_pcm, threads=_thr)
-t0 = time.perf_counter(); _orc.features_u16(_cpu_pcm, threads=_thr); tn = time.perf_counter() - t0
-res["cfg1_frontend_cpu_port"] = {"single_thread_clips_per_s": round(64 / t1, 1), "threads": _thr,
-                                 "all_threads_clips_per_s": round(256 / tn, 1), "kind": "port (oracle/microfrontend_ref.c)"}
-
 # ---- cfg2 sweep: frontend + embedding forward
 rows = []
 for B in (32, 128, 512, 1024, 2048, 4096, 8192, 16384, 65536):     # 65 536 clips = 2 GB of PCM: the asymptote
