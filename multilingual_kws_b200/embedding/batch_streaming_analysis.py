@@ -24,6 +24,13 @@ from .single_target_recognize_commands import detect_stream, detect_stream_devic
 from ..frontend import FEATURE_SCALE, float_audio_to_int16_np
 
 
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
 @dataclass(frozen=True)
 class StreamFlags:
     wav: os.PathLike
@@ -55,21 +62,38 @@ class StreamTarget:
 def stream_inferences(model, model_settings, audio: np.ndarray, sample_rate: int, clip_duration_ms: int,
                       clip_stride_ms: int, window_batch: int = 8192, keep_on_device: bool = False):
     """softmax rows [W, n_labels] for every window offset in range(0, len - clip, stride)
-    (batch_streaming_analysis.py:66-117; the chunk branches there add up to the un-chunked result)."""
+    (batch_streaming_analysis.py:66-117; the chunk branches there add up to the un-chunked result).
+
+    Under torch.distributed (one process per GPU) the window range is sharded contiguously: rank r uploads only the
+    samples its windows [W r / n, W (r+1) / n) cover, and the rows are all-gathered, so every rank returns the full
+    matrix (windows are independent; a window's features depend on its own samples only)."""
     clip = int(clip_duration_ms * sample_rate / 1000)
     stride = int(clip_stride_ms * sample_rate / 1000)
     fe = input_data._frontend_for(model_settings)
-    pcm = torch.from_numpy(float_audio_to_int16_np(audio)).cuda()
-    W = fe.stream_num_windows(pcm.numel(), clip, stride)
+    pcm_host = float_audio_to_int16_np(audio)
+    W = fe.stream_num_windows(pcm_host.shape[0], clip, stride)
     n_labels = model.head.classes if hasattr(model, "head") else model.output_dim
     if W <= 0:
         return torch.zeros((0, n_labels), device="cuda") if keep_on_device else np.zeros((0, n_labels), np.float32)
-    st = fe.stream_prepare(pcm)
+    dist = _dist()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+    lo, hi = W * rank // world, W * (rank + 1) // world
     outs = []
-    for w0 in range(0, W, window_batch):
-        feats = st.windows(clip, stride, w0, min(window_batch, W - w0), FEATURE_SCALE)
-        outs.append(model.forward_device(feats).clone())
-    probs = torch.cat(outs)
+    if hi > lo:
+        # window offsets are range(0, n - clip, stride): the last offset must be < n - clip, hence the extra sample
+        pcm = torch.from_numpy(np.ascontiguousarray(pcm_host[lo * stride:(hi - 1) * stride + clip + 1])).cuda()
+        st = fe.stream_prepare(pcm)
+        for w0 in range(0, hi - lo, window_batch):
+            feats = st.windows(clip, stride, w0, min(window_batch, hi - lo - w0), FEATURE_SCALE)
+            outs.append(model.forward_device(feats).clone())
+    probs = torch.cat(outs) if outs else torch.zeros((0, n_labels), device="cuda")
+    if dist is not None:
+        most = -(-W // world)                                     # shard sizes differ by at most one row
+        padded = torch.zeros((most, n_labels), dtype=probs.dtype, device=probs.device)
+        padded[:probs.shape[0]] = probs
+        parts = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(parts, padded)
+        probs = torch.cat([parts[r][:W * (r + 1) // world - W * r // world] for r in range(world)])
     return probs if keep_on_device else probs.cpu().numpy()
 
 

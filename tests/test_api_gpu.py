@@ -234,3 +234,16 @@ def test_grouped_steps_equal_single_steps(world):
     got = train_steps_grouped(b, batches[:4], 1e-2) + train_steps_grouped(b, batches[4:], 1e-2)
     assert got == want
     assert np.array_equal(a.head.get_params(), b.head.get_params())
+
+
+def test_streaming_sharded_over_two_gpus():
+    """Window-sharded streaming inference under torchrun (2 ranks, NCCL all-gather) == the single-process result."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dist_stream_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert "DIST_STREAM_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
