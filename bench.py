@@ -358,7 +358,7 @@ def run_ours(args, rank, local_rank, world):
 
     # the same steps the way `fit` runs them: the embedding is frozen, so G consecutive steps share ONE embedding
     # forward of G x 512 clips (transfer_learning.train_steps_grouped); timed per group, reported per step
-    ft_G = 4
+    ft_G = 8
     ft_specs_g = feats[:ft_B].repeat(ft_G, 1, 1)[:ft_G * ft_B].contiguous() if B >= ft_B else None
     ft_emb_g = torch.empty((ft_G * ft_B, emb_model.output_dim), dtype=torch.float32, device=dev)
 

@@ -111,7 +111,7 @@ def evaluate(model: FewShotModel, ds) -> Dict[str, float]:
 
 
 def fit(model: FewShotModel, train_ds, validation_data, steps_per_epoch: int, epochs: int, lr: float,
-        csvlog_dest=None, verbose=1, group_clips: int = 2048) -> Dict[str, List[float]]:
+        csvlog_dest=None, verbose=1, group_clips: int = 4096) -> Dict[str, List[float]]:
     """Keras-style fit of the head.  Steps are executed in groups that share one embedding forward of about
     `group_clips` clips (`train_steps_grouped`; group_clips = 0: one forward per step) — same updates, same history."""
     history = {"loss": [], "accuracy": [], "val_loss": [], "val_accuracy": []}

@@ -94,7 +94,7 @@ res["cfg3_finetune_100_steps_batch512"] = {
 # grouped: what fit() does — the embedding is frozen, G consecutive steps share one embedding forward
 from multilingual_kws_b200.embedding.transfer_learning import train_steps_grouped
 rows = []
-for bs, steps, G in ((512, 100, 4), (64, 256, 32)):            # config 3, and the reference's default run (run.py: 4 x 64 steps of 64)
+for bs, steps, G in ((512, 100, 8), (64, 256, 64)):            # config 3, and the reference's default run (run.py: 4 x 64 steps of 64)
     f_ = fe.forward(pcm_batch(bs, 3))[..., None]
     y_ = torch.from_numpy(np.random.default_rng(7).integers(0, 3, bs).astype(np.int32)).to(dev)
     res_row = {"batch": bs, "steps": steps, "steps_per_embedding_forward": G}
