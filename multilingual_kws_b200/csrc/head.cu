@@ -4,10 +4,11 @@
 // Replaces, for reference multilingual_kws/embedding/transfer_learning.py:47-59,86-93, what Keras
 // executes per `fit` step on the trainable part of the model (the embedding is frozen there, :43).
 //
-//   kws_head_grad        one launch: forward + loss + backward for the local batch.  Each CTA owns a tile of
-//                        32 samples (warp-cooperative 1024-long dot products, W1 staged in smem), writes its
-//                        partial gradient, and the LAST CTA to finish sums the partials in a fixed order
-//                        (deterministic) into a flat buffer  [dW1 | db1 | dW2 | db2 | loss_sum | correct | count].
+//   kws_head_grad        two launches.  (1) one warp per sample: z1 = e . W1 (W1 staged in smem), then tanh, logits,
+//                        softmax, CE on the logits, dz2, dz1 inside the warp; (2) the gradient sums over the batch,
+//                        16 input features per CTA, written in a fixed order (deterministic, no atomics) into a flat
+//                        buffer  [dW1 | db1 | dW2 | db2 | loss_sum | correct | count].  ~12 us at batch 64 ... 512 (the
+//                        first version — 32 samples per CTA, partials reduced by the last CTA — took 140 us).
 //                        Gradients are SUMS over samples so that one NCCL all-reduce(sum) of the flat buffer
 //                        over NVLink yields the global-batch gradient (+ the loss / accuracy scalars).
 //   kws_head_apply_adam  mean = flat / count, Adam (beta1 .9, beta2 .999, eps 1e-7 outside the sqrt,
@@ -15,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -27,194 +29,196 @@ using namespace kws;
 namespace {
 
 constexpr int kHeadThreads = 256;
-constexpr int kTile = 32;                 // samples per CTA
+constexpr int kSamplesPerWarp = 2;
+constexpr int kSamplesPerCta = (kHeadThreads / 32) * kSamplesPerWarp;   // 16
 constexpr int kMaxHidden = 32;
 constexpr int kMaxClasses = 8;
+constexpr int kDwK = 16;                  // input features per CTA of the dW1 kernel
+constexpr int kDwLanes = kHeadThreads / kDwK;   // sample lanes per feature
 
 struct HeadDims {
   int in_dim, hidden, classes;
   int off_b1, off_w2, off_b2, n_params;   // flat offsets
 };
 
-// ---- forward only: probs[B, classes]
-__global__ void __launch_bounds__(kHeadThreads)
-head_forward_kernel(const float* __restrict__ emb, int B, HeadDims D, const float* __restrict__ params,
-                    float* __restrict__ probs) {
-  extern __shared__ float sm[];
-  float* s_z1 = sm;                                  // [kTile][hidden]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int s0 = blockIdx.x * kTile;
-  const float* w1 = params;
-  // each warp: 4 samples x hidden units
-  for (int si = warp * 4; si < warp * 4 + 4; ++si) {
-    const int s = s0 + si;
-    for (int j = 0; j < D.hidden; ++j) {
-      float acc = 0.f;
-      if (s < B)
-        for (int k = lane; k < D.in_dim; k += 32) acc = fmaf(__ldg(emb + (size_t)s * D.in_dim + k), __ldg(w1 + (size_t)k * D.hidden + j), acc);
+__device__ __forceinline__ float warp_sum(float a) {
 #pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) s_z1[si * D.hidden + j] = acc;
-    }
-  }
+  for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+
+// ---- per-sample part: one warp per sample (two samples per warp, 16 per CTA; W1 staged in shared memory with a padded
+// pitch).  z1 = e . W1 with the lanes striding over the 1024 inputs, then the whole tail (tanh, logits, softmax, CE on
+// the logits, dz2, dz1) inside the warp: lane j holds hidden unit j, class sums are warp reductions.
+// TRAIN: writes h [B,H], dz1 [B,H], dz2 [B,C], stat [B,2] (loss, correct) for the gradient kernel; else probs [B,C].
+template <bool TRAIN, int HT>      // HT: compile-time hidden size (18 = the reference's head), 0 = run-time
+__global__ void __launch_bounds__(kHeadThreads)
+head_sample_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels, int B, HeadDims D,
+                   const float* __restrict__ params, float* __restrict__ probs, float* __restrict__ hbuf,
+                   float* __restrict__ dz1, float* __restrict__ dz2, float* __restrict__ stat) {
+  extern __shared__ float s_w1[];                        // [in_dim][hidden + 1]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = HT > 0 ? HT : D.hidden, HP = H + 1, C = D.classes;
+  constexpr int JN = HT > 0 ? HT : kMaxHidden;           // unrolled hidden units (no predicated-off slots when HT > 0)
+#pragma unroll 8
+  for (int k = warp; k < D.in_dim; k += kHeadThreads / 32)        // one W1 row (H contiguous floats) per warp and step
+    if (lane < H) s_w1[k * HP + lane] = __ldg(params + (size_t)k * H + lane);
   __syncthreads();
-  if (tid < kTile && s0 + tid < B) {
-    float h[kMaxHidden], z[kMaxClasses];
-    for (int j = 0; j < D.hidden; ++j) h[j] = tanhf(s_z1[tid * D.hidden + j] + params[D.off_b1 + j]);
-    float mx = -INFINITY;
-    for (int c = 0; c < D.classes; ++c) {
-      float a = params[D.off_b2 + c];
-      for (int j = 0; j < D.hidden; ++j) a = fmaf(h[j], params[D.off_w2 + j * D.classes + c], a);
-      z[c] = a;
-      mx = fmaxf(mx, a);
+  for (int u = 0; u < kSamplesPerWarp; ++u) {
+    const int s = blockIdx.x * kSamplesPerCta + warp * kSamplesPerWarp + u;
+    if (s >= B) break;                                   // warp-uniform
+    float acc[JN];
+#pragma unroll
+    for (int j = 0; j < JN; ++j) acc[j] = 0.f;
+    // eight independent global loads in flight per lane (a plain k loop would wait ~700 cycles for each of its 32 loads)
+    for (int k0 = lane; k0 < D.in_dim; k0 += 256) {
+      float e[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) e[q] = (k0 + 32 * q < D.in_dim) ? __ldg(emb + (size_t)s * D.in_dim + k0 + 32 * q) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (k0 + 32 * q < D.in_dim) {
+          const float* wr = s_w1 + (k0 + 32 * q) * HP;
+#pragma unroll
+          for (int j = 0; j < JN; ++j)
+            if (j < H) acc[j] = fmaf(e[q], wr[j], acc[j]);
+        }
+      }
     }
-    float sum = 0.f;
-    for (int c = 0; c < D.classes; ++c) { z[c] = expf(z[c] - mx); sum += z[c]; }
-    for (int c = 0; c < D.classes; ++c) probs[(size_t)(s0 + tid) * D.classes + c] = z[c] / sum;
+    float z1 = 0.f;                                      // lane j keeps hidden unit j
+#pragma unroll
+    for (int j = 0; j < JN; ++j)
+      if (j < H) {
+        const float a = warp_sum(acc[j]);
+        if (lane == j) z1 = a;
+      }
+    const bool unit = lane < H;
+    const float hj = unit ? tanhf(z1 + __ldg(params + D.off_b1 + lane)) : 0.f;
+    float z[kMaxClasses], mx = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < C) {
+        z[c] = warp_sum(unit ? hj * __ldg(params + D.off_w2 + lane * C + c) : 0.f) + __ldg(params + D.off_b2 + c);
+        if (z[c] > mx) { mx = z[c]; arg = c; }
+      }
+    float p[kMaxClasses], sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < C) { p[c] = expf(z[c] - mx); sum += p[c]; }
+    if (!TRAIN) {
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < kMaxClasses; ++c)
+          if (c < C) probs[(size_t)s * C + c] = p[c] / sum;
+      }
+      continue;
+    }
+    const int y = labels[s];
+    float dh = 0.f, zy = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < C) {
+        const float d = p[c] / sum - (c == y ? 1.f : 0.f);          // d(sum of losses) / dz2
+        if (c == y) zy = z[c];
+        if (unit) dh = fmaf(d, __ldg(params + D.off_w2 + lane * C + c), dh);
+        if (lane == 0) dz2[(size_t)s * C + c] = d;
+      }
+    if (unit) {
+      hbuf[(size_t)s * H + lane] = hj;
+      dz1[(size_t)s * H + lane] = dh * (1.f - hj * hj);
+    }
+    if (lane == 0) {
+      stat[(size_t)s * 2] = logf(sum) + mx - zy;                    // cross-entropy on the logits
+      stat[(size_t)s * 2 + 1] = arg == y ? 1.f : 0.f;
+    }
   }
 }
 
-// ---- forward + loss + backward; partial gradients per CTA, last CTA reduces
+// ---- gradient sums, written straight into the flat buffer [dW1 | db1 | dW2 | db2 | loss_sum | correct | count] in a
+// fixed order (deterministic).  CTAs 0 .. in_dim/16-1: dW1[k][j] = sum_s e[s][k] dz1[s][j] for 16 inputs each (16
+// sample lanes per input, combined through shared memory in lane order); the last CTA: db1, dW2, db2 and the scalars.
 __global__ void __launch_bounds__(kHeadThreads)
-head_grad_kernel(const float* __restrict__ emb, const int32_t* __restrict__ labels, int B, HeadDims D,
-                 const float* __restrict__ params, float* __restrict__ partials, unsigned int* __restrict__ counter,
-                 float* __restrict__ flat) {
-  extern __shared__ float sm[];
-  float* s_w1 = sm;                                      // [in_dim][hidden+1] (padded: conflict-free)
-  float* s_z1 = s_w1 + (size_t)D.in_dim * (D.hidden + 1);  // [kTile][hidden]  z1, later dz1
-  float* s_h = s_z1 + kTile * D.hidden;                  // [kTile][hidden]
-  float* s_dz2 = s_h + kTile * D.hidden;                 // [kTile][classes]
-  float* s_stat = s_dz2 + kTile * D.classes;             // [kTile][2] loss, correct
-  __shared__ bool is_last;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int s0 = blockIdx.x * kTile;
-  const int H = D.hidden, HP = D.hidden + 1;
-  const int flat_n = D.n_params + 3;
-  float* mine = partials + (size_t)blockIdx.x * flat_n;
-
-  for (int i = tid; i < D.in_dim * H; i += kHeadThreads) s_w1[(i / H) * HP + (i % H)] = __ldg(params + i);
-  __syncthreads();
-
-  // z1: each warp owns 4 samples; lanes stride over k, accumulate all hidden units, then warp-reduce
-  for (int si = warp * 4; si < warp * 4 + 4; ++si) {
-    const int s = s0 + si;
+head_grad_sums_kernel(const float* __restrict__ emb, int B, HeadDims D, const float* __restrict__ hbuf,
+                      const float* __restrict__ dz1, const float* __restrict__ dz2, const float* __restrict__ stat,
+                      float* __restrict__ flat) {
+  __shared__ float red[kDwLanes * kDwK * (kMaxHidden + 1)];
+  const int tid = threadIdx.x;
+  const int H = D.hidden, HP = D.hidden + 1, C = D.classes;
+  if (blockIdx.x + 1 < gridDim.x) {
+    const int kk = tid % kDwK, sl = tid / kDwK;
+    const int k = blockIdx.x * kDwK + kk;
     float acc[kMaxHidden];
 #pragma unroll
     for (int j = 0; j < kMaxHidden; ++j) acc[j] = 0.f;
-    if (s < B) {
-      for (int k = lane; k < D.in_dim; k += 32) {
-        const float e = __ldg(emb + (size_t)s * D.in_dim + k);
-        const float* wr = s_w1 + k * HP;
+    // samples in tiles of 128: the tile's dz1 rows (9 KB) are staged in shared memory once per CTA instead of being
+    // fetched from L2 by every thread (all 64 CTAs read the same rows at the same time)
+    float* s_dz = red;                                   // [128][H] (the reduction below reuses the buffer afterwards)
+    for (int t0 = 0; t0 < B; t0 += 128) {
+      const int nt = min(128, B - t0);
+      __syncthreads();
+      for (int i = tid; i < nt * H; i += kHeadThreads) s_dz[i] = __ldg(dz1 + (size_t)t0 * H + i);
+      __syncthreads();
+      if (k < D.in_dim) {
+        float e[8];
 #pragma unroll
-        for (int j = 0; j < kMaxHidden; ++j)
-          if (j < H) acc[j] = fmaf(e, wr[j], acc[j]);
+        for (int q = 0; q < 8; ++q) e[q] = (sl + kDwLanes * q < nt) ? __ldg(emb + (size_t)(t0 + sl + kDwLanes * q) * D.in_dim + k) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (sl + kDwLanes * q < nt) {
+            const float* d = s_dz + (sl + kDwLanes * q) * H;
+#pragma unroll
+            for (int j = 0; j < kMaxHidden; ++j)
+              if (j < H) acc[j] = fmaf(e[q], d[j], acc[j]);
+          }
+        }
       }
     }
-#pragma unroll
-    for (int j = 0; j < kMaxHidden; ++j) {
-      if (j < H) {
-        float a = acc[j];
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) s_z1[si * H + j] = a;
-      }
-    }
-  }
-  __syncthreads();
-
-  // per-sample tail: tanh, logits, softmax, CE on logits, dz2, dz1
-  if (tid < kTile) {
-    const int s = s0 + tid;
-    float loss = 0.f, correct = 0.f;
-    if (s < B) {
-      float h[kMaxHidden], z[kMaxClasses], p[kMaxClasses];
-      for (int j = 0; j < H; ++j) { h[j] = tanhf(s_z1[tid * H + j] + params[D.off_b1 + j]); s_h[tid * H + j] = h[j]; }
-      float mx = -INFINITY;
-      int arg = 0;
-      for (int c = 0; c < D.classes; ++c) {
-        float a = params[D.off_b2 + c];
-        for (int j = 0; j < H; ++j) a = fmaf(h[j], params[D.off_w2 + j * D.classes + c], a);
-        z[c] = a;
-        if (a > mx) { mx = a; arg = c; }
-      }
-      float sum = 0.f;
-      for (int c = 0; c < D.classes; ++c) { p[c] = expf(z[c] - mx); sum += p[c]; }
-      const int y = labels[s];
-      loss = logf(sum) + mx - z[y];
-      correct = arg == y ? 1.f : 0.f;
-      for (int c = 0; c < D.classes; ++c) {
-        const float d = p[c] / sum - (c == y ? 1.f : 0.f);      // d(sum of losses)/dz2
-        s_dz2[tid * D.classes + c] = d;
-      }
-      for (int j = 0; j < H; ++j) {
-        float dh = 0.f;
-        for (int c = 0; c < D.classes; ++c) dh = fmaf(s_dz2[tid * D.classes + c], params[D.off_w2 + j * D.classes + c], dh);
-        s_z1[tid * H + j] = dh * (1.f - h[j] * h[j]);             // dz1
-      }
-    } else {
-      for (int j = 0; j < H; ++j) { s_h[tid * H + j] = 0.f; s_z1[tid * H + j] = 0.f; }
-      for (int c = 0; c < D.classes; ++c) s_dz2[tid * D.classes + c] = 0.f;
-    }
-    s_stat[tid * 2] = loss;
-    s_stat[tid * 2 + 1] = correct;
-  }
-  __syncthreads();
-
-  // partial dW1[k][j] = sum_s e[s][k] * dz1[s][j]
-  const int ns = min(kTile, B - s0);
-  for (int k = tid; k < D.in_dim; k += kHeadThreads) {
-    float acc[kMaxHidden];
-#pragma unroll
-    for (int j = 0; j < kMaxHidden; ++j) acc[j] = 0.f;
-    for (int si = 0; si < ns; ++si) {
-      const float e = __ldg(emb + (size_t)(s0 + si) * D.in_dim + k);
-#pragma unroll
-      for (int j = 0; j < kMaxHidden; ++j)
-        if (j < H) acc[j] = fmaf(e, s_z1[si * H + j], acc[j]);
-    }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < kMaxHidden; ++j)
-      if (j < H) mine[(size_t)k * H + j] = acc[j];
-  }
-  // db1, dW2, db2, stats
-  for (int i = tid; i < H + H * D.classes + D.classes + 3; i += kHeadThreads) {
-    float a = 0.f;
-    int dst;
-    if (i < H) {
-      for (int si = 0; si < kTile; ++si) a += s_z1[si * H + i];
-      dst = D.off_b1 + i;
-    } else if (i < H + H * D.classes) {
-      const int j = (i - H) / D.classes, c = (i - H) % D.classes;
-      for (int si = 0; si < kTile; ++si) a = fmaf(s_h[si * H + j], s_dz2[si * D.classes + c], a);
-      dst = D.off_w2 + j * D.classes + c;
-    } else if (i < H + H * D.classes + D.classes) {
-      const int c = i - H - H * D.classes;
-      for (int si = 0; si < kTile; ++si) a += s_dz2[si * D.classes + c];
-      dst = D.off_b2 + c;
-    } else {
-      const int w = i - (H + H * D.classes + D.classes);
-      if (w == 2) a = (float)ns;
-      else for (int si = 0; si < kTile; ++si) a += s_stat[si * 2 + w];
-      dst = D.n_params + w;
-    }
-    mine[dst] = a;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int done = atomicAdd(counter, 1u);
-    is_last = (done == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    for (int i = tid; i < flat_n; i += kHeadThreads) {
+      if (j < H) red[(sl * kDwK + kk) * HP + j] = acc[j];
+    __syncthreads();
+    for (int o = tid; o < kDwK * H; o += kHeadThreads) {
+      const int kq = o / H, j = o - kq * H;
       float a = 0.f;
-      for (unsigned int b = 0; b < gridDim.x; ++b) a += __ldcg(partials + (size_t)b * flat_n + i);
-      flat[i] = a;
+      for (int l = 0; l < kDwLanes; ++l) a += red[(l * kDwK + kq) * HP + j];
+      if (blockIdx.x * kDwK + kq < D.in_dim) flat[(size_t)(blockIdx.x * kDwK + kq) * H + j] = a;
     }
-    if (tid == 0) *counter = 0;
+    return;
   }
+  // db1 [H], dW2 [H*C], db2 [C], loss_sum, correct: warp w sums the samples s = w (mod 8), lane l the outputs l, l + 32,
+  // l + 64 (independent loads in flight); the eight partial sums per output are combined in warp order
+  const int n_out = H + H * C + C + 2;
+  const int warp = tid >> 5, lane = tid & 31;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  auto term = [&](int o, int s) -> float {
+    if (o < H) return dz1[(size_t)s * H + o];
+    if (o < H + H * C) { const int j = (o - H) / C, c = (o - H) - j * C; return hbuf[(size_t)s * H + j] * dz2[(size_t)s * C + c]; }
+    if (o < H + H * C + C) return dz2[(size_t)s * C + (o - H - H * C)];
+    return stat[(size_t)s * 2 + (o - H - H * C - C)];
+  };
+#pragma unroll 4
+  for (int s = warp; s < B; s += kHeadThreads / 32) {
+    if (lane < n_out) a0 += term(lane, s);
+    if (lane + 32 < n_out) a1 += term(lane + 32, s);
+    if (lane + 64 < n_out) a2 += term(lane + 64, s);
+  }
+  if (lane < n_out) red[warp * n_out + lane] = a0;
+  if (lane + 32 < n_out) red[warp * n_out + lane + 32] = a1;
+  if (lane + 64 < n_out) red[warp * n_out + lane + 64] = a2;
+  __syncthreads();
+  if (tid < n_out) {
+    float t = 0.f;
+    for (int w = 0; w < kHeadThreads / 32; ++w) t += red[w * n_out + tid];
+    int dst;
+    if (tid < H) dst = D.off_b1 + tid;
+    else if (tid < H + H * C) dst = D.off_w2 + (tid - H);
+    else if (tid < H + H * C + C) dst = D.off_b2 + (tid - H - H * C);
+    else dst = D.n_params + (tid - H - H * C - C);
+    flat[dst] = t;
+  }
+  if (tid == 0) flat[D.n_params + 2] = (float)B;
 }
 
 __global__ void head_adam_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
@@ -235,9 +239,9 @@ __global__ void head_adam_kernel(float* __restrict__ params, float* __restrict__
 
 struct kws_head {
   HeadDims D;
-  float *params = nullptr, *m = nullptr, *v = nullptr, *partials = nullptr;
-  unsigned int* counter = nullptr;
-  int partial_ctas = 0;
+  float *params = nullptr, *m = nullptr, *v = nullptr;
+  float* scratch = nullptr;            // per-sample h, dz1, dz2, (loss, correct) of the last kws_head_grad batch
+  int scratch_rows = 0;
   float beta1, beta2, eps;
   long long t = 0;
 };
@@ -263,14 +267,17 @@ extern "C" int kws_head_create(kws_head_t** out, int in_dim, int hidden, int cla
   cudaError_t e = cudaMalloc(&h->params, sizeof(float) * D.n_params);
   if (e == cudaSuccess) e = cudaMalloc(&h->m, sizeof(float) * D.n_params);
   if (e == cudaSuccess) e = cudaMalloc(&h->v, sizeof(float) * D.n_params);
-  if (e == cudaSuccess) e = cudaMalloc(&h->counter, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemcpy(h->params, flat.data(), sizeof(float) * D.n_params, cudaMemcpyHostToDevice);
+  const int sample_smem = (int)(sizeof(float) * (size_t)in_dim * (hidden + 1));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(head_sample_kernel<false, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, sample_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(head_sample_kernel<true, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, sample_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(head_sample_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sample_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(head_sample_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sample_smem);
   if (e == cudaSuccess) e = cudaMemset(h->m, 0, sizeof(float) * D.n_params);
   if (e == cudaSuccess) e = cudaMemset(h->v, 0, sizeof(float) * D.n_params);
-  if (e == cudaSuccess) e = cudaMemset(h->counter, 0, sizeof(unsigned int));
   if (e != cudaSuccess) {
     set_error("kws_head_create: CUDA device required (%s); there is no CPU fallback", cudaGetErrorString(e));
-    cudaFree(h->params); cudaFree(h->m); cudaFree(h->v); cudaFree(h->counter);
+    cudaFree(h->params); cudaFree(h->m); cudaFree(h->v);
     delete h;
     return KWS_ERR_CUDA;
   }
@@ -280,7 +287,7 @@ extern "C" int kws_head_create(kws_head_t** out, int in_dim, int hidden, int cla
 
 extern "C" void kws_head_destroy(kws_head_t* h) {
   if (!h) return;
-  cudaFree(h->params); cudaFree(h->m); cudaFree(h->v); cudaFree(h->counter); cudaFree(h->partials);
+  cudaFree(h->params); cudaFree(h->m); cudaFree(h->v); cudaFree(h->scratch);
   delete h;
 }
 
@@ -288,13 +295,20 @@ extern "C" size_t kws_head_flat_size(const kws_head_t* h) { return h ? (size_t)h
 extern "C" int kws_head_num_params(const kws_head_t* h) { return h ? h->D.n_params : KWS_ERR_ARG; }
 extern "C" long long kws_head_step_count(const kws_head_t* h) { return h ? h->t : KWS_ERR_ARG; }
 
+static int head_sample_smem(const HeadDims& D) { return (int)(sizeof(float) * (size_t)D.in_dim * (D.hidden + 1)); }
+
 extern "C" int kws_head_forward(kws_head_t* h, const float* d_emb, int B, float* d_probs, void* stream) {
   KWS_REQUIRE(h && B >= 0, "kws_head_forward: bad argument");
   if (B == 0) return KWS_OK;
   KWS_REQUIRE(d_emb && d_probs, "kws_head_forward: NULL device buffer");
-  const int grid = (B + kTile - 1) / kTile;
-  head_forward_kernel<<<grid, kHeadThreads, sizeof(float) * kTile * h->D.hidden, (cudaStream_t)stream>>>(
-      d_emb, B, h->D, h->params, d_probs);
+  const int smem = head_sample_smem(h->D);
+  const int grid = (B + kSamplesPerCta - 1) / kSamplesPerCta;
+  if (h->D.hidden == 18)
+    head_sample_kernel<false, 18><<<grid, kHeadThreads, smem, (cudaStream_t)stream>>>(
+        d_emb, nullptr, B, h->D, h->params, d_probs, nullptr, nullptr, nullptr, nullptr);
+  else
+    head_sample_kernel<false, 0><<<grid, kHeadThreads, smem, (cudaStream_t)stream>>>(
+        d_emb, nullptr, B, h->D, h->params, d_probs, nullptr, nullptr, nullptr, nullptr);
   KWS_CUDA_CHECK(cudaGetLastError());
   return KWS_OK;
 }
@@ -303,18 +317,31 @@ extern "C" int kws_head_grad(kws_head_t* h, const float* d_emb, const int32_t* d
                              void* stream) {
   KWS_REQUIRE(h && B >= 1 && d_emb && d_labels && d_flat, "kws_head_grad: bad argument");
   const HeadDims& D = h->D;
-  const int grid = (B + kTile - 1) / kTile;
-  const size_t flat_n = (size_t)D.n_params + 3;
-  if (grid > h->partial_ctas) {
-    cudaFree(h->partials);
-    h->partials = nullptr;
-    KWS_CUDA_CHECK(cudaMalloc(&h->partials, sizeof(float) * flat_n * grid));
-    h->partial_ctas = grid;
+  const size_t row = (size_t)2 * D.hidden + D.classes + 2;      // h, dz1, dz2, (loss, correct) per sample
+  if (B > h->scratch_rows) {
+    cudaFree(h->scratch);
+    h->scratch = nullptr;
+    h->scratch_rows = 0;
+    const int rows = B < 1024 ? 1024 : B;
+    KWS_CUDA_CHECK(cudaMalloc(&h->scratch, sizeof(float) * row * rows));
+    h->scratch_rows = rows;
   }
-  const size_t smem = sizeof(float) * ((size_t)D.in_dim * (D.hidden + 1) + 2 * kTile * D.hidden + kTile * D.classes + kTile * 2);
-  KWS_CUDA_CHECK(cudaFuncSetAttribute(head_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  head_grad_kernel<<<grid, kHeadThreads, smem, (cudaStream_t)stream>>>(d_emb, d_labels, B, D, h->params, h->partials,
-                                                                     h->counter, d_flat);
+  float* hbuf = h->scratch;
+  float* dz1 = hbuf + (size_t)h->scratch_rows * D.hidden;
+  float* dz2 = dz1 + (size_t)h->scratch_rows * D.hidden;
+  float* stat = dz2 + (size_t)h->scratch_rows * D.classes;
+  KWS_REQUIRE(D.hidden + D.hidden * D.classes + D.classes + 2 <= 96, "kws_head_grad: head too wide for the sums kernel");
+  const int smem = head_sample_smem(D);
+  const int grid = (B + kSamplesPerCta - 1) / kSamplesPerCta;
+  if (D.hidden == 18)
+    head_sample_kernel<true, 18><<<grid, kHeadThreads, smem, (cudaStream_t)stream>>>(
+        d_emb, d_labels, B, D, h->params, nullptr, hbuf, dz1, dz2, stat);
+  else
+    head_sample_kernel<true, 0><<<grid, kHeadThreads, smem, (cudaStream_t)stream>>>(
+        d_emb, d_labels, B, D, h->params, nullptr, hbuf, dz1, dz2, stat);
+  KWS_CUDA_CHECK(cudaGetLastError());
+  head_grad_sums_kernel<<<(D.in_dim + kDwK - 1) / kDwK + 1, kHeadThreads, 0, (cudaStream_t)stream>>>(
+      d_emb, B, D, hbuf, dz1, dz2, stat, d_flat);
   KWS_CUDA_CHECK(cudaGetLastError());
   return KWS_OK;
 }
