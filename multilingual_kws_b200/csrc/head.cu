@@ -191,18 +191,26 @@ head_grad_sums_kernel(const float* __restrict__ emb, int B, HeadDims D, const fl
   // l + 64 (independent loads in flight); the eight partial sums per output are combined in warp order
   const int n_out = H + H * C + C + 2;
   const int warp = tid >> 5, lane = tid & 31;
+  // every output is sum_s p[s * sp] * q[s * sq] (q = a constant 1 for the plain sums): the index arithmetic is done once
+  // per lane, the sample loop is loads + FMAs only and is unrolled so that the loads of 8 samples are in flight
+  const float one = 1.0f;
+  const float *p[3], *q[3];
+  int sp[3], sq[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int o = lane + 32 * u;
+    p[u] = &one; q[u] = &one; sp[u] = 0; sq[u] = 0;
+    if (o < H) { p[u] = dz1 + o; sp[u] = H; }
+    else if (o < H + H * C) { const int j = (o - H) / C, c = (o - H) - j * C; p[u] = hbuf + j; sp[u] = H; q[u] = dz2 + c; sq[u] = C; }
+    else if (o < H + H * C + C) { p[u] = dz2 + (o - H - H * C); sp[u] = C; }
+    else if (o < n_out) { p[u] = stat + (o - H - H * C - C); sp[u] = 2; }
+  }
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  auto term = [&](int o, int s) -> float {
-    if (o < H) return dz1[(size_t)s * H + o];
-    if (o < H + H * C) { const int j = (o - H) / C, c = (o - H) - j * C; return hbuf[(size_t)s * H + j] * dz2[(size_t)s * C + c]; }
-    if (o < H + H * C + C) return dz2[(size_t)s * C + (o - H - H * C)];
-    return stat[(size_t)s * 2 + (o - H - H * C - C)];
-  };
-#pragma unroll 4
+#pragma unroll 8
   for (int s = warp; s < B; s += kHeadThreads / 32) {
-    if (lane < n_out) a0 += term(lane, s);
-    if (lane + 32 < n_out) a1 += term(lane + 32, s);
-    if (lane + 64 < n_out) a2 += term(lane + 64, s);
+    a0 = fmaf(p[0][(size_t)s * sp[0]], q[0][(size_t)s * sq[0]], a0);
+    a1 = fmaf(p[1][(size_t)s * sp[1]], q[1][(size_t)s * sq[1]], a1);
+    a2 = fmaf(p[2][(size_t)s * sp[2]], q[2][(size_t)s * sq[2]], a2);
   }
   if (lane < n_out) red[warp * n_out + lane] = a0;
   if (lane + 32 < n_out) red[warp * n_out + lane + 32] = a1;
