@@ -73,13 +73,21 @@ class EmbeddingModel:
 
     @classmethod
     def load(cls, path: os.PathLike, output_layer: str = "dense_2", **kw) -> "EmbeddingModel":
-        """Loads a saved weight container (directory with weights.npz, or the .npz itself) and cuts the dense tower
-        at `output_layer` (the reference cuts its classifier at "dense_2", transfer_learning.py:38-43)."""
+        """Loads a saved weight container and cuts the dense tower at `output_layer` (the reference cuts its classifier
+        at "dense_2", transfer_learning.py:38-43).  `path` is a directory holding weights.npz, the .npz itself, or a
+        Keras SavedModel directory (variables/variables.index + data shard, read without TensorFlow by savedmodel.py —
+        see the status note there)."""
         p = str(path)
+        if os.path.isdir(p) and not os.path.isfile(os.path.join(p, "weights.npz")) and \
+                os.path.isfile(os.path.join(p, "variables", "variables.index")):
+            from .savedmodel import load_keras_variables
+            w = {k: np.asarray(v, np.float32) for k, v in load_keras_variables(p).items()}
+            return cls(cut_at(w, output_layer), **kw)
         if os.path.isdir(p):
             p = os.path.join(p, "weights.npz")
         if not os.path.isfile(p):
-            raise FileNotFoundError(f"no weight container at {p} (expected a directory holding weights.npz)")
+            raise FileNotFoundError(f"no weight container at {p} (expected a directory holding weights.npz or a Keras "
+                                    "SavedModel's variables/)")
         return cls(cut_at(W.load_npz(p), output_layer), **kw)
 
     def save(self, path: os.PathLike) -> None:
