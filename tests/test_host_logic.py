@@ -201,3 +201,19 @@ def test_augment_plan_draws_match_host_augment(monkeypatch, tmp_path):
         if lb == input_data.UNKNOWN_WORD_LABEL:
             assert int(item["fg_index"]) >= 3
     assert modes == {0, 1, 2}
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints one well-formed JSON line without a GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--ref-sample", "48", "--ref-budget-s", "6"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["unit"] == "utterances/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
