@@ -1,7 +1,8 @@
 """ctypes wrapper over oracle/microfrontend_ref.c — TEST INFRASTRUCTURE ONLY.
 
 The CPU restatement of TF 2.7's ``audio_microfrontend`` op as the reference calls it in
-``multilingual_kws/embedding/input_data.py:19-35``.  PARITY UNPINNED (see the C file's header).
+``multilingual_kws/embedding/input_data.py:19-35``.  Pinned on the upstream op's own known-answer tests (see the C
+file's header and tests/test_oracle_tf_kat.py).
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
 legs may import this module.
 """

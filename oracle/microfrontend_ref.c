@@ -14,9 +14,15 @@
  * FIXED_POINT=16.  This file restates that published algorithm from the
  * public description of those sources; nothing is copied.
  *
- * PARITY UNPINNED: the reference ships no tests / golden vectors for this path and TensorFlow
- * cannot be executed in the build container, so this oracle is pinned only by closed-form table
- * checks, FFT-vs-numpy consistency and analytic invariants (tests/test_oracle_frontend.py).
+ * PINS: the reference ships no tests / golden vectors for this path and TensorFlow cannot be
+ * executed in the build container.  The oracle reproduces exactly the known-answer vectors of the
+ * upstream op's own unit tests (audio_microfrontend_op_test.py testSimple / testSimpleFloatScaled and
+ * the lib/*_test.cc chain: window, filterbank sqrt, noise reduction, PCAN, log scale) — restated from
+ * the published test files, tests/golden/tf_microfrontend_kat.json, tests/test_oracle_tf_kat.py — at
+ * the op's 1 kHz / 25 ms / 2-channel test configuration; the reference's 16 kHz / 30 ms / 40-channel
+ * configuration runs the same code and is covered by closed-form table checks, FFT-vs-numpy
+ * consistency and analytic invariants (tests/test_oracle_frontend.py).  A TensorFlow-generated vector
+ * at the production configuration is still missing.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * call into this file.
