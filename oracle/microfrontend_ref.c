@@ -17,7 +17,7 @@
  * PINS: the reference ships no tests / golden vectors for this path and TensorFlow cannot be
  * executed in the build container.  The oracle reproduces exactly the known-answer vectors of the
  * upstream op's own unit tests (audio_microfrontend_op_test.py testSimple / testSimpleFloatScaled and
- * the lib/*_test.cc chain: window, filterbank sqrt, noise reduction, PCAN, log scale) — restated from
+ * the lib/ unit-test chain (`<stage>_test.cc`): window, filterbank sqrt, noise reduction, PCAN, log scale) — restated from
  * the published test files, tests/golden/tf_microfrontend_kat.json, tests/test_oracle_tf_kat.py — at
  * the op's 1 kHz / 25 ms / 2-channel test configuration; the reference's 16 kHz / 30 ms / 40-channel
  * configuration runs the same code and is covered by closed-form table checks, FFT-vs-numpy
