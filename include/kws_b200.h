@@ -100,6 +100,11 @@ int kws_embed_set_chunk(kws_embed_t* m, int chunk);
 int kws_embed_set_chunk_late(kws_embed_t* m, int chunk);
 /* 1 (default): capture the launch list of a forward pass into a CUDA graph per (buffers, batch) and replay it */
 int kws_embed_set_graph(kws_embed_t* m, int enable);
+/* Schedule of the network's tail (blocks 4a..7a + top conv, maps of <= 7x5 pixels): 0 = layer by layer (expand GEMM,
+   depthwise + pool, SE GEMMs, gating, project GEMM: six launches per block), 1 = one fused tcgen05 launch per MBConv
+   block, 2 (default) = runs of consecutive blocks (and the top conv + average pool) per launch.  Same results up to
+   16-bit rounding of the intermediates the fused kernel keeps in fp32. */
+int kws_embed_set_fuse(kws_embed_t* m, int mode);
 /* kernel launches one forward pass of `batch` clips issues */
 int kws_embed_launches(const kws_embed_t* m, int batch);
 size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch);

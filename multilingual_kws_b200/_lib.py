@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libkws_b200.so")
+LIB_PATH = os.environ.get("KWS_LIB_PATH") or os.path.join(_HERE, "csrc", "libkws_b200.so")   # override: A/B builds
 
 c_void_p, c_int, c_float, c_size_t, c_int64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_int64
 
@@ -39,6 +39,7 @@ SIGNATURES = {
     "kws_embed_forward_timed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "kws_embed_launches": (c_int, [c_void_p, c_int]),
     "kws_embed_set_graph": (c_int, [c_void_p, c_int]),
+    "kws_embed_set_fuse": (c_int, [c_void_p, c_int]),
     "kws_embed_set_chunk_late": (c_int, [c_void_p, c_int]),
     "kws_embed_set_chunk": (c_int, [c_void_p, c_int]),
     "kws_embed_workspace_bytes": (c_size_t, [c_void_p, c_int]),

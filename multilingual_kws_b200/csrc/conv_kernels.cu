@@ -19,15 +19,8 @@ namespace kws {
 
 namespace {
 
-// sigmoid(x) = 0.5 tanh(x/2) + 0.5 with the hardware tanh: one MUFU op and three instructions per swish instead of
-// EX2 + RCP and five (the same form the GEMM epilogues use; the result is rounded to 16 bits anyway)
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float swish(float x) { const float h = 0.5f * x; return fmaf(h, tanh_approx(h), h); }
-__device__ __forceinline__ float sigmoidf(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+__device__ __forceinline__ float swish(float x) { return ptx::swish_f(x); }
+__device__ __forceinline__ float sigmoidf(float x) { return ptx::sigmoid_f(x); }
 
 // ---------------------------------------------------------------- stem
 constexpr int kStemThreads = 256;

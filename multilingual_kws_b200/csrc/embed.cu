@@ -27,6 +27,7 @@
 #include "common.h"
 #include "conv_kernels.h"
 #include "gemm_tcgen05.cuh"
+#include "mbconv_fused.h"
 
 using namespace kws;
 
@@ -92,12 +93,30 @@ struct Op {
   const float* se_b1 = nullptr;       // [se_pad]
   const uint16_t* se_w2 = nullptr;   // [C][se_pad]
   int dw_group = 1;
+  int block_id = -1;                   // MBConv block this op belongs to (index into kws_embed::fblocks), -1: none
   size_t out_elems_per_clip = 0;
   double flops_per_clip = 0;           // 2 * MACs
   double bytes_per_clip = 0;           // algorithmic: activation read + write (weights excluded)
 };
 
 }  // namespace
+
+// One MBConv block in the form the fused tail kernel wants (mbconv_fused.cu); ops [op_lo, op_hi] are its layer-wise ops.
+struct FusedBlock {
+  FusedBlockInfo info{};
+  int op_lo = 0, op_hi = 0;
+  bool fusable = false;
+  // host-side pieces the device descriptor is built from
+  const uint16_t *w_exp = nullptr, *w_se1 = nullptr, *w_se2 = nullptr, *w_proj = nullptr;
+  const float *b_exp = nullptr, *w_dw = nullptr, *b_dw = nullptr, *b_se1 = nullptr, *b_se2 = nullptr, *b_proj = nullptr;
+  int se = 0;
+};
+// A run of consecutive fusable blocks executed by one launch
+struct FusedSegment {
+  int blk_lo = 0, nblocks = 0;         // blocks [blk_lo, blk_lo + nblocks)
+  int op_lo = 0, op_hi = 0;            // layer-wise ops it replaces
+  int in_place = 0;                    // every block has a skip connection: the output may overwrite the input rows
+};
 
 struct GraphEntry {
   const float* feats; float* emb; void* ws; int batch; long long chunk;   // chunk: schedule key (chunks + SM budgets)
@@ -128,6 +147,12 @@ struct kws_embed {
   int se_via_gemm = 1;                 // wide layers: SE FCs as batched tcgen05 GEMMs (0: inside the depthwise kernel)
   int bf16 = 0;                        // 16-bit storage / tensor-core operand type: 0 fp16 (default), 1 bf16
   double flops_per_clip = 0;
+  // Fused tail (mbconv_fused.cu): 0 = layer by layer, 1 = one launch per MBConv block, 2 = runs of blocks per launch
+  int fuse = 0;                        // (default stays layer-wise until the fused kernel wins in the graph; see kws_embed_set_fuse)
+  std::vector<FusedBlock> fblocks;
+  std::vector<FusedBlockInfo> finfos;  // fblocks[i].info, contiguous (the launcher takes an array)
+  FusedBlockDev* d_fblocks = nullptr;  // device array, same order as fblocks (+ the top-conv pseudo-block at the end)
+  std::vector<FusedSegment> segs[3];   // per fuse mode
 };
 
 namespace {
@@ -199,6 +224,61 @@ struct Builder {
 };
 
 }  // namespace
+
+// Device descriptors of the fusable blocks (weight tensor maps are encoded once, here) and the launch plans of the two
+// fused modes: per block, and runs of consecutive blocks that fit one CTA's shared memory / TMEM with >= kMinGroup clips.
+static int build_fused_plan(kws_embed* m) {
+  const int n = (int)m->fblocks.size();
+  std::vector<FusedBlockDev> dev(n);
+  for (int i = 0; i < n; ++i) {
+    FusedBlock& fb = m->fblocks[i];
+    // fusion applies to the network's tail only (tiny maps); a block must also fit on its own
+    if (fb.fusable && fb.op_lo < m->tail_op) fb.fusable = false;
+    if (fb.fusable && fused_max_group(&fb.info, 1, m->max_smem) < 1) fb.fusable = false;
+    FusedBlockDev& d = dev[i];
+    memset(&d, 0, sizeof(d));
+    if (!fb.fusable) continue;
+    const FusedBlockInfo& I = fb.info;
+    int rc = make_tmap_h16(&d.tm_exp, fb.w_exp, (uint64_t)I.cexp, (uint64_t)I.cin, 128, m->bf16, 64);
+    if (rc == KWS_OK && !I.pool_out) rc = make_tmap_h16(&d.tm_se1, fb.w_se1, (uint64_t)I.se_pad, (uint64_t)I.cexp, (uint32_t)I.se_pad, m->bf16, 64);
+    if (rc == KWS_OK && !I.pool_out) rc = make_tmap_h16(&d.tm_se2, fb.w_se2, (uint64_t)I.cexp, (uint64_t)I.se_pad, 128, m->bf16, 64);
+    if (rc == KWS_OK && !I.pool_out) rc = make_tmap_h16(&d.tm_proj, fb.w_proj, (uint64_t)I.cout, (uint64_t)I.cexp, 128, m->bf16, 64);
+    if (rc != KWS_OK) return rc;
+    d.b_exp = fb.b_exp; d.w_dw = fb.w_dw; d.b_dw = fb.b_dw; d.b_se1 = fb.b_se1; d.b_se2 = fb.b_se2; d.b_proj = fb.b_proj;
+    d.cin = I.cin; d.cexp = I.cexp; d.cout = I.cout; d.se = fb.se; d.se_pad = I.se_pad; d.geom = I.geom;
+    d.pin = I.pin; d.pout = I.pout; d.residual = I.residual; d.pool_out = I.pool_out;
+  }
+  KWS_CUDA_CHECK(cudaMalloc(&m->d_fblocks, sizeof(FusedBlockDev) * (size_t)n));
+  m->dev_allocs.push_back(m->d_fblocks);
+  KWS_CUDA_CHECK(cudaMemcpy(m->d_fblocks, dev.data(), sizeof(FusedBlockDev) * (size_t)n, cudaMemcpyHostToDevice));
+  // mode 1: one launch per fusable block (the top conv stays a GEMM: it has its own well-fed tile shape)
+  for (int i = 0; i < n; ++i) {
+    const FusedBlock& fb = m->fblocks[i];
+    if (!fb.fusable || fb.info.pool_out) continue;
+    FusedSegment sg;
+    sg.blk_lo = i; sg.nblocks = 1; sg.op_lo = fb.op_lo; sg.op_hi = fb.op_hi; sg.in_place = fb.info.residual;
+    m->segs[1].push_back(sg);
+  }
+  // mode 2: greedy runs.  A run keeps growing while the merged launch still fits at least kMinGroup clips per CTA.
+  const int kMinGroup = 7;
+  m->finfos.resize(n);
+  for (int i = 0; i < n; ++i) m->finfos[i] = m->fblocks[i].info;
+  const std::vector<FusedBlockInfo>& infos = m->finfos;
+  for (int i = 0; i < n;) {
+    if (!m->fblocks[i].fusable || m->fblocks[i].info.pool_out) { ++i; continue; }
+    int cnt = 1;
+    while (i + cnt < n && m->fblocks[i + cnt].fusable && m->fblocks[i + cnt].op_lo == m->fblocks[i + cnt - 1].op_hi + 1 &&
+           fused_max_group(&infos[i], cnt + 1, m->max_smem) >= kMinGroup)
+      ++cnt;
+    FusedSegment sg;
+    sg.blk_lo = i; sg.nblocks = cnt; sg.op_lo = m->fblocks[i].op_lo; sg.op_hi = m->fblocks[i + cnt - 1].op_hi;
+    sg.in_place = 1;
+    for (int q = 0; q < cnt; ++q) if (!m->fblocks[i + q].info.residual) sg.in_place = 0;
+    m->segs[2].push_back(sg);
+    i += cnt;
+  }
+  return KWS_OK;
+}
 
 extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t bytes, int act_dtype) {
   KWS_REQUIRE(out && blob, "kws_embed_create: NULL argument");
@@ -285,6 +365,13 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
       const int cin = r == 0 ? c.fin : c.fout;
       const int cexp = cin * c.e, cout = c.fout;
       const int se = cin / 4 > 1 ? cin / 4 : 1;
+      FusedBlock fb;
+      fb.op_lo = (int)m->ops.size();
+      fb.info.cin = cin; fb.info.cexp = cexp; fb.info.cout = cout; fb.info.pin = h * w; fb.info.pool_out = 0;
+      fb.info.residual = (stride == 1 && cin == cout) ? 1 : 0;
+      fb.se = se;
+      fb.fusable = c.e != 1 && !pend_k;          // needs its own expansion (a folded pair feeds the expand GEMM from D)
+      const int block_id = (int)m->fblocks.size();
       if (c.e != 1) {
         std::vector<float> sc, sh;
         CK(B.bn(n + "_expand_bn", cexp, &sc, &sh));
@@ -314,6 +401,8 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
         CK(op.w && op.bias);
         op.out_elems_per_clip = (size_t)h * w * cexp;
         macs += (double)h * w * op.K * cexp;
+        op.block_id = block_id;
+        fb.w_exp = op.w; fb.b_exp = op.bias;
         m->ops.push_back(op);
       }
       {
@@ -347,7 +436,11 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
         P.b_se2 = B.vec(std::vector<float>(b2->data, b2->data + cexp));
         CK(P.w_dw && P.b_dw && P.w_se1 && P.b_se1 && P.w_se2 && P.b_se2);
         P.se_external = 0; P.pooled_out = nullptr;
-        if (cexp > 256 && m->se_via_gemm) {     // C <= 256 runs the in-kernel (narrow) squeeze-excite
+        fb.info.geom = fused_geom_id(k, stride, h, w, P.pad_top, P.pad_left);
+        fb.info.pout = P.Ho * P.Wo;
+        if (!fb.info.geom) fb.fusable = false;
+        const bool wide_se = cexp > 256 && m->se_via_gemm;   // C <= 256 runs the in-kernel (narrow) squeeze-excite
+        if (wide_se || fb.fusable) {
           // wide layer: SE as two batched tensor-core GEMMs.  FC1: [B,C] x W1[se_pad,C]^T (+b1, swish);
           // FC2: [B,se_pad] x W2[C,se_pad]^T (+b2, sigmoid).  Padding rows / columns are zero.
           const int sp = (se + 15) & ~15;
@@ -360,12 +453,16 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
               w2h[(size_t)ch * sp + j] = B.h16(w2->data[(size_t)j * cexp + ch]);
             }
           }
-          P.se_external = 1;
+          P.se_external = wide_se ? 1 : 0;
           op.se_pad = sp;
           op.se_w1 = B.vec16(w1h); op.se_b1 = B.vec(b1p); op.se_w2 = B.vec16(w2h);
           CK(op.se_w1 && op.se_b1 && op.se_w2);
-          if ((size_t)cexp > m->max_se_channels) m->max_se_channels = (size_t)cexp;
+          if (wide_se && (size_t)cexp > m->max_se_channels) m->max_se_channels = (size_t)cexp;
+          fb.info.se_pad = sp;
+          fb.w_se1 = op.se_w1; fb.b_se1 = op.se_b1; fb.w_se2 = op.se_w2;
         }
+        fb.w_dw = P.w_dw; fb.b_dw = P.b_dw; fb.b_se2 = P.b_se2;
+        op.block_id = block_id;
         op.dw_group = dwse_pick_group(P, m->max_smem, 1 << 20, m->sm_count);
         if (op.dw_group < 1) { B.err = "depthwise layer " + n + " does not fit shared memory"; return fail(KWS_ERR_UNSUPPORTED); }
         macs += (double)P.Ho * P.Wo * cexp * k * k + 2.0 * cexp * se;
@@ -388,6 +485,9 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
             for (int q = 0; q < cexp; ++q) pend_w[(size_t)o * cexp + q] = (double)kp->data[(size_t)q * cout + o] * sc[o];
           }
           pend_k = cexp;
+          fb.fusable = false;
+          fb.op_hi = (int)m->ops.size() - 1;
+          m->fblocks.push_back(fb);
           continue;
         }
         Op op;
@@ -399,7 +499,11 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
         CK(op.w && op.bias);
         op.out_elems_per_clip = (size_t)h * w * cout;
         macs += (double)h * w * cexp * cout;
+        op.block_id = block_id;
+        fb.w_proj = op.w; fb.b_proj = op.bias;
+        fb.op_hi = (int)m->ops.size();
         m->ops.push_back(op);
+        m->fblocks.push_back(fb);
       }
     }
   }
@@ -416,7 +520,15 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
     CK(op.w && op.bias);
     op.out_elems_per_clip = 1280;
     macs += 4.0 * 320 * 1280;
+    FusedBlock fb;
+    fb.op_lo = fb.op_hi = (int)m->ops.size();
+    fb.info.cin = 320; fb.info.cexp = 1280; fb.info.cout = 1280; fb.info.pin = 4; fb.info.pout = 4; fb.info.pool_out = 1;
+    fb.info.geom = 7; fb.info.residual = 0; fb.info.se_pad = 0;
+    fb.w_exp = op.w; fb.b_exp = op.bias;
+    fb.fusable = true;
+    op.block_id = (int)m->fblocks.size();
     m->ops.push_back(op);
+    m->fblocks.push_back(fb);
   }
   // ---- dense tower: dense, dense_1, ... (relu ... relu, last = selu), cut at the last one present
   {
@@ -493,6 +605,15 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
   for (size_t i = 0; i < m->ops.size(); ++i)
     if (m->ops[i].name == "block3b_out") m->tail_op = (int)i + 1;
   m->flops_per_clip = 2.0 * macs;
+  if (const char* env = getenv("KWS_FUSE")) m->fuse = atoi(env) < 0 ? 0 : (atoi(env) > 2 ? 2 : atoi(env));
+  {
+    const int rc = build_fused_plan(m);
+    if (rc != KWS_OK) {
+      for (void* p : m->dev_allocs) cudaFree(p);
+      delete m;
+      return rc;
+    }
+  }
   *out = m;
   return KWS_OK;
 }
@@ -558,10 +679,19 @@ extern "C" int kws_embed_launches(const kws_embed_t* m, int batch) {
   const int n_ops = (int)m->ops.size();
   int launches = 0;
   for (int i = 0; i < n_ops; ++i) {
-    const int per = (m->ops[i].kind == kOpDwse && m->ops[i].dw.se_external) ? 4 : 1;   // dw+pool, 2 SE GEMMs, gating
+    int per = (m->ops[i].kind == kOpDwse && m->ops[i].dw.se_external) ? 4 : 1;   // dw+pool, 2 SE GEMMs, gating
+    for (const FusedSegment& c : m->segs[m->fuse])
+      if (i >= c.op_lo && i <= c.op_hi) per = i == c.op_hi ? 1 : 0;               // one launch for the whole run
     launches += per * (i < m->split_op ? (batch + ce - 1) / ce : (batch + cl - 1) / cl);
   }
   return launches;
+}
+
+// 0: layer-by-layer schedule; 1: one fused launch per MBConv block of the tail; 2 (default): runs of blocks per launch
+extern "C" int kws_embed_set_fuse(kws_embed_t* m, int mode) {
+  KWS_REQUIRE(m != nullptr && mode >= 0 && mode <= 2, "kws_embed_set_fuse: bad argument");
+  m->fuse = mode;
+  return KWS_OK;
 }
 
 extern "C" int kws_embed_set_graph(kws_embed_t* m, int enable) {
@@ -599,7 +729,7 @@ static int embed_forward_impl(kws_embed_t* m, const float* d_feats, int batch, f
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (m->use_graph && tap_op < 0 && !host_op_ms && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
       cap == cudaStreamCaptureStatusNone) {
-    const long long sched_key = (((long long)m->chunk * 100003 + m->chunk_late) * 1024 + sm_head) * 1024 + sm_tail;
+    const long long sched_key = ((((long long)m->chunk * 100003 + m->chunk_late) * 1024 + sm_head) * 1024 + sm_tail) * 4 + m->fuse;
     for (auto& g : m->graphs)
       if (g.feats == d_feats && g.emb == d_emb && g.ws == d_workspace && g.batch == batch && g.chunk == sched_key) {
         KWS_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
@@ -636,6 +766,11 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
   const int sms_tail = (sm_tail > 0 && sm_tail < m->sm_count) ? sm_tail : m->sm_count;
   const int n_ops = (int)m->ops.size();
   const int chunk_seg[2] = {batch < m->chunk ? batch : m->chunk, batch < m->chunk_late ? batch : m->chunk_late};
+  // a tap inside a fused run (not its last op) needs the layer-wise schedule
+  int fuse_mode = m->fuse;
+  if (tap_op >= 0)
+    for (const FusedSegment& c : m->segs[fuse_mode])
+      if (tap_op >= c.op_lo && tap_op < c.op_hi) fuse_mode = 0;
   // workspace carve-up: [Xe | Ee | De] (early chunk) [H = late X, whole batch] [El | Dl] (late chunk)
   uint16_t* base = static_cast<uint16_t*>(d_workspace);
   uint16_t* early[3];
@@ -675,9 +810,38 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
       if (sgi == 0) { bufs[0] = early[0]; bufs[1] = early[1]; bufs[2] = early[2]; }
       else { bufs[0] = H + m->buf_elems[1][0] * (size_t)b0; bufs[1] = late_e; bufs[2] = late_d; }
       if (host_op_ms) { KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st)); ev_op.push_back(-1); }
+      int trunk = 0;                    // buffer holding the current block input: 0 = X, 2 = D (after a fused launch)
       for (int oi = op_lo; oi < op_hi; ++oi) {
         const Op& op = m->ops[oi];
         const int sms = oi >= m->tail_op ? sms_tail : sms_head;
+        const FusedSegment* sg = nullptr;
+        if (sgi == 1)
+          for (const FusedSegment& c : m->segs[fuse_mode])
+            if (c.op_lo == oi) sg = &c;
+        if (sg) {
+          // a run of MBConv blocks (and possibly the top conv) in one launch: mbconv_fused.cu
+          const Op& lastop = m->ops[sg->op_hi];
+          void* in_ptr = bufs[trunk];
+          void* outp;
+          if (lastop.out_buf != 0) outp = bufs[lastop.out_buf];
+          else if (sg->in_place) outp = in_ptr;
+          else { trunk = trunk == 0 ? 2 : 0; outp = bufs[trunk]; }
+          const int rcf = launch_mbconv_fused(in_ptr, nb, m->d_fblocks + sg->blk_lo, m->finfos.data() + sg->blk_lo,
+                                              sg->nblocks, outp, m->bf16, sms, m->max_smem, st);
+          if (rcf != KWS_OK) return rcf;
+          if (host_op_ms) { KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st)); ev_op.push_back(sg->op_hi); }
+          if (sg->op_hi == tap_op && d_tap)
+            KWS_CUDA_CHECK(cudaMemcpyAsync(static_cast<uint8_t*>(d_tap) + (size_t)b0 * lastop.out_elems_per_clip * 2, outp,
+                                           (size_t)nb * lastop.out_elems_per_clip * 2, cudaMemcpyDeviceToDevice, st));
+          oi = sg->op_hi;
+          continue;
+        }
+        if (trunk != 0 && (op.in_buf == 0 || op.res_buf == 0)) {
+          // a layer-wise op follows a fused launch that left the trunk in the D buffer: bring it back to X
+          const size_t el = m->ops[oi - 1].out_elems_per_clip;
+          KWS_CUDA_CHECK(cudaMemcpyAsync(bufs[0], bufs[2], (size_t)nb * el * 2, cudaMemcpyDeviceToDevice, st));
+          trunk = 0;
+        }
         void* out_ptr = op.out_buf >= 0 ? (void*)bufs[op.out_buf] : (void*)(d_emb + (size_t)b0 * m->out_dim);
         if (sgi == 0 && oi == m->split_op - 1 && op.out_buf == 0)      // hand-off: early chunk -> late X (whole batch)
           out_ptr = H + m->buf_elems[1][0] * (size_t)b0;

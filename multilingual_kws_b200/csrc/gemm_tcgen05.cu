@@ -23,20 +23,24 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int block_k, int 
   return L;
 }
 
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
+// swish / sigmoid: one tanh.approx per element (ptx::swish_f / sigmoid_f; -DKWS_SWISH_EXACT: EX2 + RCP).  The tanh form
+// takes h = 0.5 (acc + bias): the bias vector is stored pre-halved in shared memory so h is ONE fma(acc, 0.5, bias/2).
+__device__ __forceinline__ bool act_halves_bias(int act) {
+#ifndef KWS_SWISH_EXACT
+  return act == kActSwish || act == kActSigmoid;
+#else
+  (void)act;
+  return false;
+#endif
 }
-// sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5: one MUFU op instead of EX2 + RCP (the result is rounded to 16 bits anyway).
-// swish / sigmoid need h = 0.5 (acc + bias): the bias vector is stored pre-halved in shared memory for these two
-// activations, so h is ONE fma(acc, 0.5, bias/2) per element — bit-identical to 0.5f * (acc + bias) (scaling by a power
-// of two is exact) and one instruction less.
-__device__ __forceinline__ bool act_halves_bias(int act) { return act == kActSwish || act == kActSigmoid; }
 __device__ __forceinline__ float bias_act(float acc, float b, int act) {      // b = bias, or bias / 2 (see above)
-  if (act == kActSwish) { const float h = fmaf(acc, 0.5f, b); return fmaf(h, tanh_approx(h), h); }
-  if (act == kActSigmoid) return fmaf(0.5f, tanh_approx(fmaf(acc, 0.5f, b)), 0.5f);
+#ifndef KWS_SWISH_EXACT
+  if (act == kActSwish) { const float h = fmaf(acc, 0.5f, b); float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h)); return fmaf(h, t, h); }
+  if (act == kActSigmoid) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(fmaf(acc, 0.5f, b))); return fmaf(0.5f, t, 0.5f); }
+#endif
   const float x = acc + b;
+  if (act == kActSwish) return ptx::swish_f(x);
+  if (act == kActSigmoid) return ptx::sigmoid_f(x);
   if (act == kActRelu) return fmaxf(x, 0.0f);
   if (act == kActSelu) return x > 0.0f ? 1.0507009873554805f * x : 1.7580993408473766f * (__expf(x) - 1.0f);
   return x;

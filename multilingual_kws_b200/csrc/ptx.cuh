@@ -143,6 +143,34 @@ __device__ __forceinline__ uint32_t umma_idesc_h16_f32(int m, int n, int fmt) {
          ((uint32_t)(m >> 4) << 24);
 }
 
+// ---- swish / sigmoid.  Default: sigmoid(x) = 0.5 tanh(x / 2) + 0.5 with the hardware tanh (one MUFU op, relative error
+// 2^-11 = the size of the 16-bit rounding the result gets anyway).  -DKWS_SWISH_EXACT selects 1 / (1 + 2^(-x log2 e))
+// as EX2 + RCP (two MUFU ops, relative error ~2^-22): measured on the B200 it changes the embedding's cosine against the
+// fp32 oracle in the sixth decimal (0.999914 vs 0.999909 on the trained-like net) and costs 6 % of the forward pass
+// (profiles/README.md, round 2), so it is not the default.
+__device__ __forceinline__ float sigmoid_f(float x) {
+#ifndef KWS_SWISH_EXACT
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(0.5f * x));
+  return fmaf(0.5f, y, 0.5f);
+#else
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+#endif
+}
+__device__ __forceinline__ float swish_f(float x) {
+#ifndef KWS_SWISH_EXACT
+  const float h = 0.5f * x;
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(h));
+  return fmaf(h, y, h);
+#else
+  return x * sigmoid_f(x);
+#endif
+}
+
 // ---- 16-bit storage helpers: two values per 32-bit word; bf = 1 -> bfloat16, 0 -> IEEE half (saturating)
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi, int bf) {
   uint32_t r;

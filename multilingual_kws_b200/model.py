@@ -117,6 +117,10 @@ class EmbeddingModel:
     def set_graph(self, enable: bool) -> None:
         _lib.check(_lib.lib().kws_embed_set_graph(self._h, int(bool(enable))))
 
+    def set_fuse(self, mode: int) -> None:
+        """Tail schedule: 0 layer by layer, 1 one fused launch per MBConv block, 2 runs of blocks per launch (default)."""
+        _lib.check(_lib.lib().kws_embed_set_fuse(self._h, int(mode)))
+
     def op_names(self):
         L = _lib.lib()
         out = []
