@@ -239,10 +239,10 @@ static int build_fused_plan(kws_embed* m) {
     memset(&d, 0, sizeof(d));
     if (!fb.fusable) continue;
     const FusedBlockInfo& I = fb.info;
-    int rc = make_tmap_h16(&d.tm_exp, fb.w_exp, (uint64_t)I.cexp, (uint64_t)I.cin, 128, m->bf16, 64);
+    int rc = make_tmap_h16(&d.tm_exp, fb.w_exp, (uint64_t)I.cexp, (uint64_t)I.cin, kFusedBoxRows, m->bf16, 64);
     if (rc == KWS_OK && !I.pool_out) rc = make_tmap_h16(&d.tm_se1, fb.w_se1, (uint64_t)I.se_pad, (uint64_t)I.cexp, (uint32_t)I.se_pad, m->bf16, 64);
-    if (rc == KWS_OK && !I.pool_out) rc = make_tmap_h16(&d.tm_se2, fb.w_se2, (uint64_t)I.cexp, (uint64_t)I.se_pad, 128, m->bf16, 64);
-    if (rc == KWS_OK && !I.pool_out) rc = make_tmap_h16(&d.tm_proj, fb.w_proj, (uint64_t)I.cout, (uint64_t)I.cexp, 128, m->bf16, 64);
+    if (rc == KWS_OK && !I.pool_out) rc = make_tmap_h16(&d.tm_se2, fb.w_se2, (uint64_t)I.cexp, (uint64_t)I.se_pad, kFusedBoxRows, m->bf16, 64);
+    if (rc == KWS_OK && !I.pool_out) rc = make_tmap_h16(&d.tm_proj, fb.w_proj, (uint64_t)I.cout, (uint64_t)I.cexp, kFusedBoxRows, m->bf16, 64);
     if (rc != KWS_OK) return rc;
     d.b_exp = fb.b_exp; d.w_dw = fb.w_dw; d.b_dw = fb.b_dw; d.b_se1 = fb.b_se1; d.b_se2 = fb.b_se2; d.b_proj = fb.b_proj;
     d.cin = I.cin; d.cexp = I.cexp; d.cout = I.cout; d.se = fb.se; d.se_pad = I.se_pad; d.geom = I.geom;

@@ -54,12 +54,15 @@ constexpr int kRegsControl = 32;
 constexpr int kRegsCompute = 112;
 constexpr uint32_t kStageBytes = 128 * 64 * 2;                 // one A tile: 128 channels x 64 k (SWIZZLE_128B)
 constexpr int kMaxStages = 8;
-constexpr int kFcN = 16;                                        // clips per CTA (rows of the pooled / squeeze operands)
+constexpr int kFcN = 16;                                        // max clips per CTA; N of the excite MMAs
 constexpr int kFc1Cols = 64;                                    // TMEM columns of the squeeze result (se_pad <= 64)
+constexpr int kBoxRows = kFusedBoxRows;                        // rows per TMA box of a 128-row weight tile: the CTAs of a
+                                                                // cluster (1, 2 or 4) each fetch 4 / C boxes and multicast them
 
 struct FusedSmem {
   uint32_t x_off, d_off, pool_off, s_off, ring_off, bar_off, total;
   int stages;
+  int fc_rows;             // rows per k-block of the pooled operand: 8 when G <= 8, else 16
 };
 
 // barrier slots (uint64_t each) at bar_off
@@ -205,6 +208,27 @@ __device__ __forceinline__ uint32_t sw_off(int row, int cchunk, int clow2) {
   return (uint32_t)(row * 128 + (((cchunk ^ row) & 7) << 4) + clow2);
 }
 
+// ---- cluster helpers: weight tiles are fetched once per cluster and multicast into every CTA's ring
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* desc, uint64_t* bar, void* dst_smem, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(ptx::smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   ptx::smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ compute warps
 struct ComputeCtx {
   uint32_t smem;           // shared-space address of the (1024-byte aligned) dynamic shared memory
@@ -229,11 +253,13 @@ __device__ __forceinline__ void compute_block(ComputeCtx& cx, const KernelArgs& 
   constexpr int K = Gm::K, S = Gm::S, H = Gm::H, W = Gm::W, PT = Gm::PT, PL = Gm::PL, HO = Gm::HO, WO = Gm::WO;
   constexpr int PIN = H * W, POUT = HO * WO;
   constexpr int PIN4 = (PIN + 3) & ~3, POUT4 = (POUT + 3) & ~3;
+  constexpr int NB = 1;     // clips per iteration (2: both TMEM loads share one wait — measured slower: register spills)
   const int cexp = blk->cexp, cout = blk->cout;
   const BlockDims d = block_dims(blk->cin, cexp, cout, PIN, POUT, blk->pool_out, cx.G);
   const uint32_t par = (uint32_t)bi & 1u;
   const uint32_t s_d = cx.smem + a.L.d_off, s_pool = cx.smem + a.L.pool_off, s_s = cx.smem + a.L.s_off,
                  s_x = cx.smem + a.L.x_off;
+  const uint32_t pool_kb = (uint32_t)a.L.fc_rows * 128u;
   const int bf = cx.bf16;
   uint64_t* const bars = cx.bars;
   const uint32_t tmem_base = cx.tmem_base;
@@ -264,37 +290,48 @@ __device__ __forceinline__ void compute_block(ComputeCtx& cx, const KernelArgs& 
     ptx::tc_fence_after();
     const int kb = c >> 6, cchunk = (c & 63) >> 3, clow2 = (c & 7) * 2;
     const uint32_t dk = s_d + (uint32_t)(kb * d.rpad_out * 128);
-    for (int g = cx.sub; g < cx.gn; g += 4) {
-      uint32_t raw[PIN4];
-      tmem_ld_cols<PIN4>(tmem_base + col_st + (uint32_t)(g * PIN), raw);
+    // one clip of this thread's channel: activation of the expansion, depthwise taps, activation, D + pooled mean
+    auto clip = [&](const uint32_t (&raw)[PIN4], int g) {
+      float x[PIN];
+#pragma unroll
+      for (int q = 0; q < PIN; ++q) x[q] = ptx::swish_f(__uint_as_float(raw[q]) + Wt.be);
+      if constexpr (GEOM == 7) {
+        // top conv: swish + global average pool, straight to global memory [clip][cexp]
+        const float m = 0.25f * ((x[0] + x[1]) + (x[2] + x[3]));
+        a.out[(size_t)(cx.g0 + g) * cexp + c] = to_h16(m, bf);
+      } else {
+        float sum = 0.0f;
+#pragma unroll
+        for (int ho = 0; ho < HO; ++ho)
+#pragma unroll
+          for (int wo = 0; wo < WO; ++wo) {
+            float acc = Wt.bd;
+#pragma unroll
+            for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+              for (int kw = 0; kw < K; ++kw) {
+                const int r = ho * S + kh - PT, cl = wo * S + kw - PL;       // compile-time after unrolling
+                if (r >= 0 && r < H && cl >= 0 && cl < W) acc = fmaf(x[r * W + cl], Wt.w[kh * K + kw], acc);
+              }
+            acc = ptx::swish_f(acc);
+            sum += acc;
+            sts_u16(dk + sw_off(g * POUT + ho * WO + wo, cchunk, clow2), to_h16(acc, bf));
+          }
+        sts_u16(s_pool + (uint32_t)kb * pool_kb + sw_off(g, cchunk, clow2), to_h16(sum * (1.0f / (float)POUT), bf));
+      }
+    };
+    for (int g = cx.sub; g < cx.gn; g += 4 * NB) {
+      uint32_t raw0[PIN4], raw1[NB == 2 ? PIN4 : 4];
+      const bool two = NB == 2 && g + 4 < cx.gn;        // warp-uniform
+      tmem_ld_cols<PIN4>(tmem_base + col_st + (uint32_t)(g * PIN), raw0);
+      if constexpr (NB == 2) {
+        if (two) tmem_ld_cols<PIN4>(tmem_base + col_st + (uint32_t)((g + 4) * PIN), raw1);
+      }
       ptx::tmem_ld_wait();
       if (valid) {
-        float x[PIN];
-#pragma unroll
-        for (int q = 0; q < PIN; ++q) x[q] = ptx::swish_f(__uint_as_float(raw[q]) + Wt.be);
-        if constexpr (GEOM == 7) {
-          // top conv: swish + global average pool, straight to global memory [clip][cexp]
-          const float m = 0.25f * ((x[0] + x[1]) + (x[2] + x[3]));
-          a.out[(size_t)(cx.g0 + g) * cexp + c] = to_h16(m, bf);
-        } else {
-          float sum = 0.0f;
-#pragma unroll
-          for (int ho = 0; ho < HO; ++ho)
-#pragma unroll
-            for (int wo = 0; wo < WO; ++wo) {
-              float acc = Wt.bd;
-#pragma unroll
-              for (int kh = 0; kh < K; ++kh)
-#pragma unroll
-                for (int kw = 0; kw < K; ++kw) {
-                  const int r = ho * S + kh - PT, cl = wo * S + kw - PL;       // compile-time after unrolling
-                  if (r >= 0 && r < H && cl >= 0 && cl < W) acc = fmaf(x[r * W + cl], Wt.w[kh * K + kw], acc);
-                }
-              acc = ptx::swish_f(acc);
-              sum += acc;
-              sts_u16(dk + sw_off(g * POUT + ho * WO + wo, cchunk, clow2), to_h16(acc, bf));
-            }
-          sts_u16(s_pool + (uint32_t)(kb * (kFcN * 128)) + sw_off(g, cchunk, clow2), to_h16(sum * (1.0f / (float)POUT), bf));
+        clip(raw0, g);
+        if constexpr (NB == 2) {
+          if (two) clip(raw1, g + 4);
         }
       }
     }
@@ -320,7 +357,7 @@ __device__ __forceinline__ void compute_block(ComputeCtx& cx, const KernelArgs& 
   if (cx.lane == 0) ptx::mbar_arrive(bars + kBarPoolReady);
   if (dbg) dbg[1] = clock64();
 
-  // ---- 2. squeeze: s[g][j] = swish(W1^T pooled + b1)
+  // ---- 2. squeeze: s[g][j] = swish(pooled . W1 + b1)
   bar_wait(bars + kBarFc1Full, par);
   ptx::tc_fence_after();
   if (dbg) dbg[2] = clock64();
@@ -355,17 +392,20 @@ __device__ __forceinline__ void compute_block(ComputeCtx& cx, const KernelArgs& 
   bar_wait(bars + kBarFc2Full, par);
   ptx::tc_fence_after();
   if (dbg) dbg[3] = clock64();
-  const uint32_t s_gate = s_pool;                       // [kFcN][cexp] 16-bit, plain row-major
+  const uint32_t s_gate = s_pool;                       // [G][cexp] 16-bit, plain row-major
   for (int j = 0; j < d.nchunk; ++j) {
     const int c = j * 128 + cx.chl;
     const bool valid = c < cexp;
     const float b2 = valid ? __ldg(blk->b_se2 + c) : 0.0f;
-    for (int g = cx.sub; g < cx.gn; g += 4) {
-      uint32_t raw;
-      tmem_ld_x1(tmem_base + d.col_fc2 + (uint32_t)(j * kFcN + g), raw);
-      ptx::tmem_ld_wait();
-      if (valid) sts_u16(s_gate + (uint32_t)(g * cexp + c) * 2u, to_h16(ptx::sigmoid_f(__uint_as_float(raw) + b2), bf));
-    }
+    uint32_t raw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)                          // this warp's clips sub, sub + 4, ...: all loads, one wait
+      if (cx.sub + 4 * i < cx.gn) tmem_ld_x1(tmem_base + d.col_fc2 + (uint32_t)(j * kFcN + cx.sub + 4 * i), raw[i]);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (valid && cx.sub + 4 * i < cx.gn)
+        sts_u16(s_gate + (uint32_t)((cx.sub + 4 * i) * cexp + c) * 2u, to_h16(ptx::sigmoid_f(__uint_as_float(raw[i]) + b2), bf));
   }
   ptx::tc_fence_before();
   compute_sync();
@@ -400,22 +440,23 @@ __device__ __forceinline__ void compute_block(ComputeCtx& cx, const KernelArgs& 
     const float bp = valid ? __ldg(blk->b_proj + c) : 0.0f;
     const int kb = c >> 6, cchunk = (c & 63) >> 3, clow2 = (c & 7) * 2;
     const uint32_t xin = s_x + (uint32_t)(kb * d.npad_in * 128), xout = s_x + (uint32_t)(kb * next_npad_in * 128);
-    for (int g = cx.sub; g < cx.gn; g += 4) {
-      uint32_t raw[POUT4];
-      tmem_ld_cols<POUT4>(tmem_base + d.col_proj + (uint32_t)(o * d.npad_out + g * POUT), raw);
-      ptx::tmem_ld_wait();
-      if (valid) {
+    auto clip_out = [&](const uint32_t (&raw)[POUT4], int g) {
 #pragma unroll
-        for (int p = 0; p < POUT; ++p) {
-          const int row = g * POUT + p;
-          float v = __uint_as_float(raw[p]) + bp;
-          if (blk->residual)      // the block's input tile: same rows, same channel (cin == cout, pin == pout)
-            v += from_h16(lds_u16(xin + sw_off(row, cchunk, clow2)), bf);
-          const uint16_t h = to_h16(v, bf);
-          if (last) a.out[((size_t)(cx.g0 + g) * POUT + p) * cout + c] = h;
-          else sts_u16(xout + sw_off(row, cchunk, clow2), h);
-        }
+      for (int p = 0; p < POUT; ++p) {
+        const int row = g * POUT + p;
+        float v = __uint_as_float(raw[p]) + bp;
+        if (blk->residual)      // the block's input tile: same rows, same channel (cin == cout, pin == pout)
+          v += from_h16(lds_u16(xin + sw_off(row, cchunk, clow2)), bf);
+        const uint16_t h = to_h16(v, bf);
+        if (last) a.out[((size_t)(cx.g0 + g) * POUT + p) * cout + c] = h;
+        else sts_u16(xout + sw_off(row, cchunk, clow2), h);
       }
+    };
+    for (int g = cx.sub; g < cx.gn; g += 4) {
+      uint32_t raw0[POUT4];
+      tmem_ld_cols<POUT4>(tmem_base + d.col_proj + (uint32_t)(o * d.npad_out + g * POUT), raw0);
+      ptx::tmem_ld_wait();
+      if (valid) clip_out(raw0, g);
     }
   }
   if (!last) {
@@ -436,7 +477,9 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const KernelArgs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages = a.L.stages;
   const int g0 = blockIdx.x * a.G;
-  const int gn = min(a.G, a.batch - g0);
+  const int gn = max(0, min(a.G, a.batch - g0));        // 0 for the padding CTAs of the last cluster
+  const int csize = (int)cluster_nctarank(), crank = (int)cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmap_x);
@@ -446,7 +489,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const KernelArgs
     if (lane == 0) {
       for (int s = 0; s < kMaxStages; ++s) {
         ptx::mbar_init(bars + kBarFull + s, 1);
-        ptx::mbar_init(bars + kBarEmpty + s, 1);
+        ptx::mbar_init(bars + kBarEmpty + s, (uint32_t)csize);   // one (multicast) commit from every CTA of the cluster
       }
       ptx::mbar_init(bars + kBarXFull, 1);
       ptx::mbar_init(bars + kBarXReady, kFusedComputeWarps);
@@ -465,12 +508,13 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const KernelArgs
     __syncwarp();
     ptx::tmem_alloc(tmem_ptr_smem, 512);
   }
-  // the pooled operand's rows beyond the clips of this CTA and the squeeze operand must hold finite values
+  // clear the pooled / squeeze operands once (rows without a clip only feed accumulator lanes nobody reads)
   for (uint32_t i = threadIdx.x * 16u; i < a.L.ring_off - a.L.pool_off; i += kFusedThreads * 16u)
     *reinterpret_cast<uint4*>(smem + a.L.pool_off + i) = make_uint4(0u, 0u, 0u, 0u);
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();                    // every CTA's barriers exist before a peer signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   ptx::pdl_launch_dependents();
@@ -491,43 +535,44 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const KernelArgs
         for (int kb = 0; kb < d.kb_in; ++kb)
           ptx::tma_load_2d(&tmap_x, bars + kBarXFull, smem + a.L.x_off + (size_t)kb * d.npad_in * 128, kb * 64, g0 * b0->pin);
       }
+      // A ring stage is filled by all CTAs of the cluster together: this CTA waits until every CTA has released the
+      // stage (its own empty barrier counts one commit per CTA), arms its own full barrier with the whole stage's
+      // bytes and fetches its share of the boxes, which TMA writes into the same stage of every CTA in the cluster.
       auto acquire = [&](uint32_t bytes) -> uint8_t* {
         bar_wait(bars + kBarEmpty + stage, phase ^ 1u);
         ptx::mbar_expect_tx(bars + kBarFull + stage, bytes);
         return smem + a.L.ring_off + (size_t)stage * kStageBytes;
       };
       auto advance = [&]() { if (++stage == stages) { stage = 0; phase ^= 1u; } };
+      auto load = [&](const CUtensorMap* tm, uint8_t* dst, int c0, int c1) {
+        if (csize > 1) tma_load_2d_mc(tm, bars + kBarFull + stage, dst, c0, c1, cmask);
+        else ptx::tma_load_2d(tm, bars + kBarFull + stage, dst, c0, c1);
+      };
+      // a 128-row x 64-column weight tile = four boxes of 32 rows; box q belongs to CTA q % csize
+      auto load_tile = [&](const CUtensorMap* tm, int c0, int row0) {
+        uint8_t* dst = acquire(kStageBytes);
+        for (int q = crank; q < 128 / kBoxRows; q += csize)
+          load(tm, dst + (size_t)q * (kBoxRows * 128), c0, row0 + q * kBoxRows);
+        advance();
+      };
       for (int bi = 0; bi < a.nblocks; ++bi) {
         const FusedBlockDev* blk = a.blocks + bi;
         const BlockDims d = block_dims(blk->cin, blk->cexp, blk->cout, blk->pin, blk->pout, blk->pool_out, a.G);
         for (int j = 0; j < d.nchunk; ++j)
-          for (int kb = 0; kb < d.kb_in; ++kb) {
-            uint8_t* dst = acquire(kStageBytes);
-            ptx::tma_load_2d(&blk->tm_exp, bars + kBarFull + stage, dst, kb * 64, j * 128);
-            advance();
-          }
+          for (int kb = 0; kb < d.kb_in; ++kb) load_tile(&blk->tm_exp, kb * 64, j * 128);
         if (blk->pool_out) continue;
-        // squeeze weights: se_pad rows per k-block, several k-blocks share one ring stage
+        // squeeze weights: se_pad rows per k-block, several k-blocks share one ring stage (one box each)
         const uint32_t sub_bytes = (uint32_t)blk->se_pad * 128u;
         const int pack = (int)(kStageBytes / sub_bytes);
         for (int kb0 = 0; kb0 < d.kb_exp; kb0 += pack) {
           const int n = min(pack, d.kb_exp - kb0);
           uint8_t* dst = acquire(sub_bytes * (uint32_t)n);
-          for (int i = 0; i < n; ++i)
-            ptx::tma_load_2d(&blk->tm_se1, bars + kBarFull + stage, dst + (size_t)i * sub_bytes, (kb0 + i) * 64, 0);
+          for (int i = crank; i < n; i += csize) load(&blk->tm_se1, dst + (size_t)i * sub_bytes, (kb0 + i) * 64, 0);
           advance();
         }
-        for (int j = 0; j < d.nchunk; ++j) {
-          uint8_t* dst = acquire(kStageBytes);
-          ptx::tma_load_2d(&blk->tm_se2, bars + kBarFull + stage, dst, 0, j * 128);
-          advance();
-        }
+        for (int j = 0; j < d.nchunk; ++j) load_tile(&blk->tm_se2, 0, j * 128);
         for (int o = 0; o < d.nout; ++o)
-          for (int kb = 0; kb < d.kb_exp; ++kb) {
-            uint8_t* dst = acquire(kStageBytes);
-            ptx::tma_load_2d(&blk->tm_proj, bars + kBarFull + stage, dst, kb * 64, o * 128);
-            advance();
-          }
+          for (int kb = 0; kb < d.kb_exp; ++kb) load_tile(&blk->tm_proj, kb * 64, o * 128);
       }
     } else if (warp == 1 && lane == 0) {
       // ===================== MMA issuer =====================
@@ -536,16 +581,22 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const KernelArgs
       uint32_t exp_use0 = 0u, exp_use1 = 0u;
       const int fmt = a.bf16 ? 1 : 0;
       const uint32_t ring = ptx::smem_u32(smem + a.L.ring_off);
+      const uint32_t pool_kb = (uint32_t)a.L.fc_rows * 128u;
+      long long* const idbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
+      long long starve = 0;                   // debug: cycles this thread waited for TMA data
       auto wait_stage = [&]() -> uint32_t {
+        const long long t0 = idbg ? clock64() : 0;
         bar_wait(bars + kBarFull + stage, phase);
+        if (idbg) starve += clock64() - t0;
         ptx::tc_fence_after();
         return ring + (uint32_t)stage * kStageBytes;
       };
-      auto release_stage = [&]() {
-        ptx::tc_commit(bars + kBarEmpty + stage);
+      auto release_stage = [&]() {            // the stage may be refilled once the MMAs of EVERY CTA have read it
+        if (csize > 1) tc_commit_mc(bars + kBarEmpty + stage, cmask);
+        else ptx::tc_commit(bars + kBarEmpty + stage);
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       };
-      // `steps` MMAs of K = 16: A = 128 rows at a_addr (weights), B = the k-block at b_addr (activations)
+      // `steps` MMAs of K = 16: A = 128 rows at a_addr, B = N rows at b_addr (both K-major SWIZZLE_128B k-blocks)
       auto mmas = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, int steps, uint32_t idesc, bool first_kb) {
         const uint64_t a_desc = ptx::umma_desc_kmajor(a_addr, 128);
         const uint64_t b_desc = ptx::umma_desc_kmajor(b_addr, 128);
@@ -592,9 +643,9 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const KernelArgs
           for (int i = 0; i < n; ++i) {
             const int kb = kb0 + i;
             const int steps = min(4, (blk->cexp - kb * 64 + 15) >> 4);
-            // A = pooled means (clips on the accumulator's lanes: 16 real rows, the rest of the 128 reads whatever
+            // A = pooled means (clips on the accumulator's lanes: <= 16 real rows, the rest of the 128 reads whatever
             // follows in shared memory and lands in lanes nobody reads), B = se_pad rows of W1^T
-            mmas(tmem_base + d.col_fc1, pool_addr + (uint32_t)(kb * kFcN * 128), sa + (uint32_t)i * sub_bytes, steps, idesc_se,
+            mmas(tmem_base + d.col_fc1, pool_addr + (uint32_t)kb * pool_kb, sa + (uint32_t)i * sub_bytes, steps, idesc_se,
                  kb == 0);
           }
           release_stage();
@@ -623,6 +674,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const KernelArgs
             release_stage();
           }
         ptx::tc_commit(bars + kBarProjFull);
+        if (idbg) { idbg[bi * 8 + 7] = starve; starve = 0; }
       }
     }
     __syncwarp();
@@ -656,6 +708,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const KernelArgs
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();                    // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -664,6 +717,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const KernelArgs
 
 FusedSmem fused_smem(const FusedBlockInfo* blocks, int nblocks, int G, int max_smem) {
   FusedSmem L;
+  L.fc_rows = G <= 8 ? 8 : 16;
   uint32_t x_bytes = 0, d_bytes = 0, pool_bytes = 0;
   for (int i = 0; i < nblocks; ++i) {
     const FusedBlockInfo& b = blocks[i];
@@ -671,9 +725,10 @@ FusedSmem fused_smem(const FusedBlockInfo* blocks, int nblocks, int G, int max_s
     x_bytes = max(x_bytes, (uint32_t)(d.kb_in * d.npad_in * 128));
     if (!b.pool_out) {
       d_bytes = max(d_bytes, (uint32_t)(d.kb_exp * d.rpad_out * 128 + 1024));   // + one 8-row group: N is padded to 16
-      pool_bytes = max(pool_bytes, (uint32_t)(d.kb_exp * kFcN * 128));
+      pool_bytes = max(pool_bytes, (uint32_t)(d.kb_exp * L.fc_rows * 128));    // also holds the [G][cexp] gate table
     }
   }
+  pool_bytes = (pool_bytes + 1023u) & ~1023u;
   L.x_off = 0;
   L.d_off = x_bytes;
   L.pool_off = L.d_off + d_bytes;
@@ -731,10 +786,20 @@ int launch_mbconv_fused(const void* d_x, int batch, const FusedBlockDev* d_block
   KWS_REQUIRE(nblocks >= 1 && d_blocks && h_blocks && d_x && d_out, "mbconv_fused: bad argument");
   const int gmax = fused_max_group(h_blocks, nblocks, max_smem);
   KWS_REQUIRE(gmax >= 1, "mbconv_fused: block does not fit shared memory / TMEM");
-  // one CTA per SM when the batch allows it: G = ceil(batch / SMs), capped by what fits
-  int G = (batch + sm_count - 1) / sm_count;
+  // KWS_FUSED_CLUSTER = 2 / 4: clusters of CTAs share every weight tile (one L2 read per cluster, multicast into all
+  // rings).  Measured on the B200: identical phase times for 1, 2 and 4 — the weight stream is not what bounds the
+  // kernel (the issuer is: a tcgen05.mma with both operands in shared memory costs ~148 cycles whatever N is, see
+  // tools/microbench/mma_chain.cu), so the default stays 1 (all 148 SMs; clusters of 4 fit only 132).
+  static const int cluster_env = [] { const char* e = getenv("KWS_FUSED_CLUSTER"); return e ? atoi(e) : 0; }();
+  int C = (cluster_env == 2 || cluster_env == 4) ? cluster_env : 1;
+  const int slots = C == 4 ? (sm_count * 132) / 148 : sm_count;
+  // one CTA per SM when the batch allows it: G = ceil(batch / resident CTAs), capped by what fits
+  int G = (batch + slots - 1) / (slots > 0 ? slots : 1);
   if (G > gmax) G = gmax;
   if (G < 1) G = 1;
+  int grid = (batch + G - 1) / G;
+  if (grid < 2 * C) C = 1;                              // tiny batches: nothing to share
+  grid = (grid + C - 1) / C * C;                        // padding CTAs run the weight pipeline without clips
   KernelArgs a;
   a.blocks = d_blocks; a.nblocks = nblocks; a.batch = batch; a.G = G; a.bf16 = bf16;
   a.L = fused_smem(h_blocks, nblocks, G, max_smem);
@@ -753,17 +818,32 @@ int launch_mbconv_fused(const void* d_x, int batch, const FusedBlockDev* d_block
   int rc = make_tmap_h16(&tx, d_x, (uint64_t)batch * b0.pin, (uint64_t)b0.cin, (uint32_t)d0.npad_in, bf16, 64);
   if (rc != KWS_OK) return rc;
   KWS_CUDA_CHECK(cudaFuncSetAttribute(mbconv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.L.total));
-  const int grid = (batch + G - 1) / G;
-  KWS_CUDA_CHECK(launch_pdl(mbconv_fused_kernel, dim3(grid), dim3(kFusedThreads), (size_t)a.L.total, st, tx, a));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = (size_t)a.L.total; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (C > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)C; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  KWS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mbconv_fused_kernel, tx, a));
   if (debug) {
     long long h[8 * 32];
     KWS_CUDA_CHECK(cudaStreamSynchronize(st));
     KWS_CUDA_CHECK(cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
     for (int b = 0; b < nblocks && b < 32; ++b) {
       const long long* t = h + b * 8;
-      fprintf(stderr, "fused blk %d (cexp %d pin %d G %d grid %d stages %d smem %u): dw %lld | fc1 wait %lld | s+fc2 wait %lld | "
-              "gate %lld | proj wait %lld | epi %lld  (cycles, CTA 0)\n", b, h_blocks[b].cexp, h_blocks[b].pin, G, grid,
-              a.L.stages, a.L.total, t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5]);
+      fprintf(stderr, "fused blk %d (cexp %d pin %d G %d grid %d cluster %d stages %d smem %u): dw %lld | fc1 wait %lld | "
+              "s+fc2 wait %lld | gate %lld | proj wait %lld | epi %lld | TMA-starved %lld (cycles, CTA 0)\n", b, h_blocks[b].cexp,
+              h_blocks[b].pin, G, grid, C, a.L.stages, a.L.total, t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3],
+              t[5] - t[4], t[6] - t[5], t[7]);
     }
   }
   return KWS_OK;

@@ -8,11 +8,13 @@ namespace kws {
 
 // Device-resident description of one MBConv block (built once at kws_embed_create; the four tensor maps describe the
 // block's constant 16-bit weight matrices, so a forward pass encodes only the activation map).
+constexpr int kFusedBoxRows = 32;   // rows per TMA box of the 128-row weight tiles (4 boxes per tile, split over a cluster)
+
 struct alignas(64) FusedBlockDev {
-  CUtensorMap tm_exp;    // expand   [cexp][cin]     (BN scale folded), box 128 x 64
+  CUtensorMap tm_exp;    // expand   [cexp][cin]     (BN scale folded), box kFusedBoxRows x 64
   CUtensorMap tm_se1;    // se_reduce [se_pad][cexp]                     box se_pad x 64
-  CUtensorMap tm_se2;    // se_expand [cexp][se_pad]                     box 128 x 64
-  CUtensorMap tm_proj;   // project  [cout][cexp]    (BN scale folded), box 128 x 64
+  CUtensorMap tm_se2;    // se_expand [cexp][se_pad]                     box kFusedBoxRows x 64
+  CUtensorMap tm_proj;   // project  [cout][cexp]    (BN scale folded), box kFusedBoxRows x 64
   const float* b_exp;    // [cexp]  expand BN shift
   const float* w_dw;     // [k*k][cexp] depthwise kernel * BN scale
   const float* b_dw;     // [cexp]  depthwise BN shift
