@@ -153,6 +153,44 @@ int kws_head_grad(kws_head_t* h, const float* d_emb, const int32_t* d_labels, in
 int kws_head_apply_adam(kws_head_t* h, const float* d_flat, float lr, void* stream);
 int kws_head_get_params(const kws_head_t* h, float* host_out);
 int kws_head_reset_optimizer(kws_head_t* h);
+/* d(sum of losses) / d(embedding) [B, in_dim] fp32 of the batch of the last kws_head_grad call: what flows into the
+   embedding when its top layers train too (transfer_learning.py:97-112, backprop_into_embedding=True). */
+int kws_head_input_grad(kws_head_t* h, int B, float* d_demb, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fine-tune backward through the top of the embedding — replaces what Keras / TensorFlow autodiff executes in the
+ * second xfer.fit of transfer_learn (multilingual_kws/embedding/transfer_learning.py:97-112: "unfreeze the top 20
+ * layers while leaving BatchNorm layers frozen" + Adam(embedding_lr)) for those 20 layers: block7a, top_conv, the
+ * dense tower.  All contractions (forward, data gradient, weight gradient) are kws_gemm_h16 calls; these are the
+ * kernels between them.  16-bit tensors are IEEE half; activation gradients carry a static loss scale.
+ * --------------------------------------------------------------------------------------------- */
+int kws_train_transpose_h16(const void* d_in, int rows, int cols, void* d_out, void* stream);   /* out[c][r] = in[r][c] */
+int kws_train_swish_fwd(const void* d_z, size_t n, void* d_a, void* stream);
+int kws_train_gap_swish_fwd(const void* d_t, int B, int P, int C, void* d_h0, void* stream);    /* mean_p swish(t) */
+int kws_train_gap_swish_bwd(const void* d_dh0, const void* d_t, int B, int P, int C, void* d_dt, void* stream);
+/* depthwise conv of a <= 7x7 map (TF SAME for stride 1, correct_pad + VALID for stride 2), NHWC 16-bit:
+   z = conv(e) * folded BN + shift, d = swish(z), pooled[b][c] = mean_p d */
+int kws_train_dw_fwd(const void* d_e, const float* d_w, const float* d_shift, int B, int C, int H, int W, int K, int S,
+                     int pad_top, int pad_left, void* d_z, void* d_d, void* d_pooled, void* stream);
+size_t kws_train_dw_bwd_scratch_floats(int B, int C, int K);
+/* dz = (dd + dp / P_out) * swish'(z); de = conv^T(dz) (16-bit); dw [K*K][C] fp32 = sum over the batch (fixed order) */
+int kws_train_dw_bwd(const void* d_dd, const void* d_dp, const void* d_z, const void* d_e, const float* d_w, int B, int C,
+                     int H, int W, int K, int S, int pad_top, int pad_left, void* d_de, float* d_dw, float* d_scratch,
+                     void* stream);
+int kws_train_gate_fwd(const void* d_d, const void* d_g, int B, int P, int C, void* d_out, void* stream);   /* d * g[b][c] */
+/* dd = ddg * g; dgpre[b][c] = (sum_p ddg * d) * g (1 - g) */
+int kws_train_gate_bwd(const void* d_ddg, const void* d_d, const void* d_g, int B, int P, int C, void* d_dd,
+                       void* d_dgpre, void* stream);
+/* dz = scale * dy * act'(ref): kind 0 relu (ref = its fp16 output), 1 selu (dy and ref = fp32: the embedding and the
+   head's input gradient), 2 swish (ref = fp16 pre-activation) */
+int kws_train_act_bwd(int kind, const void* d_dy, const void* d_ref, size_t n, float scale, void* d_dz, void* stream);
+int kws_train_colsum(const void* d_x, int rows, int cols, float* d_out, void* stream);          /* fp32 bias gradient */
+/* Keras Adam (eps outside the sqrt, bias-corrected step) on an fp32 master [n / cols][cols]: the gradient is a SUM over
+   the global batch with respect to the BN-folded weight, g = grad * row_scale[row] / (*d_count * loss_scale);
+   d_out16 / d_out32 (optional) receive the folded 16-bit / fp32 copy the forward kernels read. */
+int kws_train_adam(float* d_param, float* d_m, float* d_v, const float* d_grad, size_t n, int cols, const float* d_row_scale,
+                   const float* d_count, float loss_scale, float lr, long long step, float beta1, float beta2, float eps,
+                   void* d_out16, float* d_out32, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Streaming post-processor — replaces the per-window Python loop

@@ -59,6 +59,22 @@ SIGNATURES = {
     "kws_head_apply_adam": (c_int, [c_void_p, c_void_p, c_float, c_void_p]),
     "kws_head_get_params": (c_int, [c_void_p, c_void_p]),
     "kws_head_reset_optimizer": (c_int, [c_void_p]),
+    "kws_head_input_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "kws_train_transpose_h16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "kws_train_swish_fwd": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "kws_train_gap_swish_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "kws_train_gap_swish_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "kws_train_dw_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kws_train_dw_bwd_scratch_floats": (c_size_t, [c_int, c_int, c_int]),
+    "kws_train_dw_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kws_train_gate_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "kws_train_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "kws_train_act_bwd": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_void_p]),
+    "kws_train_colsum": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "kws_train_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_float, c_float,
+                               ctypes.c_longlong, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "kws_stream_detect": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_double, ctypes.c_double, c_int, c_void_p,
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "kws_augment_pcm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,

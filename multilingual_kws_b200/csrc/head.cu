@@ -354,6 +354,31 @@ extern "C" int kws_head_grad(kws_head_t* h, const float* d_emb, const int32_t* d
   return KWS_OK;
 }
 
+// d(sum of losses) / d(embedding) of the batch of the last kws_head_grad call: demb[s][k] = sum_j dz1[s][j] W1[k][j].
+// Needed when the layers below the head train too (transfer_learn phase 2, reference transfer_learning.py:97-112).
+__global__ void __launch_bounds__(256) head_input_grad_kernel(const float* __restrict__ dz1, const float* __restrict__ params,
+                                                              int B, int in_dim, int H, float* __restrict__ demb) {
+  const size_t n = (size_t)B * in_dim;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const size_t s = i / in_dim, k = i - s * in_dim;
+    const float* w = params + k * H;
+    const float* d = dz1 + s * H;
+    float a = 0.f;
+    for (int j = 0; j < H; ++j) a = fmaf(d[j], __ldg(w + j), a);
+    demb[i] = a;
+  }
+}
+
+extern "C" int kws_head_input_grad(kws_head_t* h, int B, float* d_demb, void* stream) {
+  KWS_REQUIRE(h && d_demb && B >= 1 && B <= h->scratch_rows, "kws_head_input_grad: call kws_head_grad on the same batch first");
+  const float* dz1 = h->scratch + (size_t)h->scratch_rows * h->D.hidden;
+  const size_t n = (size_t)B * h->D.in_dim;
+  const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  head_input_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dz1, h->params, B, h->D.in_dim, h->D.hidden, d_demb);
+  KWS_CUDA_CHECK(cudaGetLastError());
+  return KWS_OK;
+}
+
 extern "C" int kws_head_apply_adam(kws_head_t* h, const float* d_flat, float lr, void* stream) {
   KWS_REQUIRE(h && d_flat, "kws_head_apply_adam: bad argument");
   h->t += 1;

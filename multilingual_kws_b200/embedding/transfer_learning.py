@@ -31,6 +31,20 @@ def _dist():
     return None
 
 
+def shared_seed() -> Optional[int]:
+    """Under torch.distributed every rank must start from the SAME head and draw the SAME global batches (each then
+    computes its shard of them): rank 0 draws a seed and broadcasts it.  Single process: None (fresh entropy, like the
+    reference's unseeded Keras initialisers / tf.data shuffles)."""
+    dist = _dist()
+    if dist is None:
+        return None
+    t = torch.zeros(1, dtype=torch.int64, device="cuda")
+    if dist.get_rank() == 0:
+        t[0] = int(np.random.SeedSequence().generate_state(1)[0])
+    dist.broadcast(t, src=0)
+    return int(t.item())
+
+
 def train_step(model: FewShotModel, specs: torch.Tensor, labels: torch.Tensor, lr: float):
     """One optimisation step on a GLOBAL batch (every rank passes the same batch; each computes its shard).
     Returns (mean loss, accuracy) of the global batch as python floats."""
@@ -176,7 +190,8 @@ def transfer_learn(
     embedding.trainable = False
 
     CATEGORIES = 3  # silence + unknown + target_keyword
-    xfer = FewShotModel(embedding, Head.keras_init(embedding.output_dim, 18, CATEGORIES))
+    seed = shared_seed()          # identical head initialisation and batch draws on every rank (None: single process)
+    xfer = FewShotModel(embedding, Head.keras_init(embedding.output_dim, 18, CATEGORIES, seed=seed))
 
     audio_dataset = input_data.AudioDataset(
         model_settings=model_settings,
@@ -185,6 +200,7 @@ def transfer_learn(
         unknown_files=unknown_files,
         unknown_percentage=UNKNOWN_PERCENTAGE,
         spec_aug_params=input_data.SpecAugParams(percentage=80),
+        seed=seed,
         device_augment=True,      # clips decoded once into a device bank; shift / mix / masks run on the GPU
     )
     init_train_ds = audio_dataset.init_single_target(AUTOTUNE, train_files, is_training=True)
