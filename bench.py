@@ -32,6 +32,11 @@ if ROOT not in sys.path:
 
 METRIC = "utterances/sec (1s@16kHz) embed-fwd"
 UNIT = "utterances/s"
+
+
+def workload(batch: int) -> str:
+    """config.workload: the SAME string in both arms (the driver compares them)."""
+    return f"configs[1]: log-mel frontend + EfficientNet-B0 embedding forward, batch {batch} x 1 s @ 16 kHz clips per GPU"
 FRONTEND_BYTES_PER_CLIP = 39840          # 32 000 B int16 PCM in + 49*40*4 B features out (SURVEY.md §8d)
 
 
@@ -167,8 +172,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32 (CPU)", "data": "synthetic",
-        "config": {"workload": f"configs[1]: frontend + EfficientNet-B0 embedding forward, batch {args.batch} x 1 s clips",
-                   "sample_clips_per_step": B},
+        "config": {"workload": workload(args.batch), "sample_clips_per_step": B},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -374,6 +378,122 @@ def run_ours(args, rank, local_rank, world):
     if ft_specs_g is not None:
         ms_ft_group, _ = timed(group_ft, max(args.steps // ft_G, 3), 3)
 
+    # ---- phase 2 of transfer_learn (BASELINE config 3: "head + last block"): forward + backward through block7a, the top
+    # conv and the dense tower + head, ONE all-reduce of the flat fp32 gradient buffer (~10.1 M floats), Adam
+    from multilingual_kws_b200.finetune import TailTrainer
+    ft2_head = Head.keras_init(emb_model.output_dim, 18, 3, seed=1)
+    trainer = TailTrainer(emb_model, ft2_head)
+    ft2_labels = ft_labels[rank * ft_B:(rank + 1) * ft_B]
+
+    def step_ft2():
+        trainer.forward_tail(trainer.tail_input(ft_specs), keep=True)
+        trainer.backward(ft2_labels)
+        if world > 1:
+            dist.all_reduce(trainer.flat, op=dist.ReduceOp.SUM)
+        trainer.apply_adam(1e-4)
+
+    ms_ft2, _ = timed(step_ft2, max(args.steps // 2, 5), 3)
+    ms_ar = None
+    if world > 1:
+        ms_ar, _ = timed(lambda: dist.all_reduce(trainer.flat, op=dist.ReduceOp.SUM), 10, 3)
+
+    # ---- N > 1: asserted parity of the multi-rank paths against the same work done by one rank (the driver's pytest box
+    # has one GPU, so this is where the NCCL paths are checked under the driver); any mismatch fails the run
+    parity = None
+    if world > 1:
+        from multilingual_kws_b200.embedding.batch_streaming_analysis import stream_inferences
+        from multilingual_kws_b200.embedding.input_data import standard_microspeech_model_settings
+        from multilingual_kws_b200.embedding.transfer_learning import train_step_embedding, train_steps_grouped
+        from multilingual_kws_b200.synthetic import synthetic_stream
+        g = torch.Generator(device="cpu").manual_seed(77)
+        nb_ = 8 * world
+        p_specs = fe.forward(torch.from_numpy(synthetic_pcm(nb_, cfg_id=9)).to(dev))          # same global batch on every rank
+        p_labels = torch.randint(0, 3, (nb_,), generator=g, dtype=torch.int32).to(dev)
+        # (1) head fine-tune, 10 grouped steps: sharded + all-reduce vs the whole batch on this rank alone
+        m_dist = FewShotModel(emb_model, Head.keras_init(emb_model.output_dim, 18, 3, seed=5))
+        m_solo = FewShotModel(emb_model, Head.keras_init(emb_model.output_dim, 18, 3, seed=5))
+        train_steps_grouped(m_dist, [(p_specs, p_labels)] * 10, 1e-3)
+        e_all = emb_model.forward_device(p_specs)
+        for _ in range(10):
+            m_solo.head.apply_adam(m_solo.head.grad(e_all, p_labels), 1e-3)
+        a, b = m_dist.head.get_params(), m_solo.head.get_params()
+        head_diff = float(np.abs(a - b).max())
+        # (2) phase-2 steps: sharded + 40 MB all-reduce vs the whole batch on this rank alone
+        t_dist = TailTrainer(emb_model, Head.keras_init(emb_model.output_dim, 18, 3, seed=6))
+        t_solo = TailTrainer(emb_model, Head.keras_init(emb_model.output_dim, 18, 3, seed=6))
+        for _ in range(3):
+            train_step_embedding(t_dist, p_specs, p_labels, 1e-4)
+            t_solo.forward_tail(t_solo.tail_input(p_specs), keep=True)
+            t_solo.backward(p_labels)
+            t_solo.apply_adam(1e-4)
+        tail_rel = 0.0
+        for pd, ps in zip(t_dist.params, t_solo.params):
+            tail_rel = max(tail_rel, float((pd.master - ps.master).norm()) / max(float(ps.master.norm()), 1e-12))
+        # (3) streaming: window range sharded over the ranks + all-gather vs unsharded
+        settings = standard_microspeech_model_settings(3)
+        audio = synthetic_stream(16000 * 20, cfg_id=5).astype(np.float32) / np.float32(32768)
+        rows_dist = stream_inferences(m_solo, settings, audio, 16000, 1000, 100)
+        import multilingual_kws_b200.embedding.batch_streaming_analysis as bsa
+        saved = bsa._dist
+        bsa._dist = lambda: None                       # the same call, un-sharded, on this rank
+        rows_solo = stream_inferences(m_solo, settings, audio, 16000, 1000, 100)
+        bsa._dist = saved
+        stream_equal = bool(np.array_equal(rows_dist, rows_solo))
+        ok = head_diff < 1e-5 and tail_rel < 1e-3 and stream_equal
+        flags = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        parity = {"finetune_parity_vs_single_rank": bool(head_diff < 1e-5), "head_param_max_abs_diff_after_10_steps": head_diff,
+                  "phase2_parity_vs_single_rank": bool(tail_rel < 1e-3), "phase2_param_max_rel_diff_after_3_steps": tail_rel,
+                  "streaming_sharded_equals_unsharded": stream_equal, "all_ranks_ok": bool(flags.item() == 1.0),
+                  "note": "sums over shards are added by NCCL in a different order than one rank adds them: equal to fp32 rounding"}
+        if flags.item() != 1.0:
+            if rank == 0:
+                print(json.dumps({"error": "multi-rank parity check failed", "parity": parity}), file=sys.stderr)
+            dist.barrier()
+            dist.destroy_process_group()
+            sys.exit(3)
+
+    # ---- the other BASELINE configurations as extra keys (driver-run): config 1 (frontend only, batch 32) and config 5
+    # (30 min of audio, 1 s window, the reference's default 20 ms hop and BASELINE's 100 ms hop)
+    extra = None
+    if rank == 0:
+        from multilingual_kws_b200.synthetic import synthetic_stream
+        from multilingual_kws_b200.frontend import FEATURE_SCALE as FS
+        extra = {}
+        pcm32 = torch.from_numpy(synthetic_pcm(32, cfg_id=1)).to(dev)
+        out32 = torch.empty((32, 49, 40), dtype=torch.float32, device=dev)
+        ms32, _ = timed(lambda: fe.forward(pcm32, out=out32), 20, 3) if world == 1 else (None, None)
+        if ms32:
+            extra["config1_frontend_only_batch32"] = {"ms": ms32, "clips_per_s": 32 / ms32 * 1e3,
+                                                      "note": "one launch, 32 CTAs: latency-bound (bit-exact vs the oracle: tests)"}
+        if world == 1:
+            n_s = 30 * 60 * 16000
+            audio_d = torch.from_numpy(synthetic_stream(n_s, cfg_id=5)).to(dev)
+            rowsx = {}
+            for hop_ms, hop in ((100, 1600), (20, 320)):
+                Wn = fe.stream_num_windows(n_s, 16000, hop)
+
+                def offline():
+                    st_ = fe.stream_prepare(audio_d)
+                    return [ft_model.forward_device(st_.windows(16000, hop, w0, min(4096, Wn - w0), FS)) for w0 in range(0, Wn, 4096)]
+                offline()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                pr_ = torch.cat(offline()).cpu()
+                wall_ = time.perf_counter() - t0
+                rowsx[f"hop_{hop_ms}ms"] = {"windows": int(Wn), "wall_s": wall_, "windows_per_s": Wn / wall_,
+                                            "realtime_factor": n_s / 16000 / wall_}
+            st_ = fe.stream_prepare(audio_d)
+            lat_ = []
+            for i in range(1, 251):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ft_model.forward_device(st_.windows(16000, 1600, i, 1, FS)).cpu()
+                lat_.append((time.perf_counter() - t0) * 1e3)
+            rowsx["online_one_window_per_100ms_hop"] = {"p50_ms": float(np.percentile(lat_[50:], 50)), "p99_ms": float(np.percentile(lat_[50:], 99))}
+            extra["config5_streaming_30min"] = rowsx
+            del audio_d
+
     # ---- per-kernel shares (CUDA events around every launch, on the launch stream) -> roofline of the dominant kernel
     peaks = load_peaks()
     roof, shares = None, None
@@ -418,7 +538,12 @@ def run_ours(args, rank, local_rank, world):
                 roof["other_roof"] = dict(bound="hbm", achieved=hbm_gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=hbm_gbs / peaks["hbm_gbs"])
             else:
                 roof["other_roof"] = tensor
+        # per-op events are taken with plain launches (no graph, no overlap of a kernel's prologue with its predecessor),
+        # so they add up to more than the graph-replayed step; the in-step figures scale them to the timed step
         roof["per_kernel_ms"] = {k: round(v["ms"], 4) for k, v in agg.items()}
+        roof["per_kernel_ms_in_step"] = {k: round(v["ms"] / total * ms_step, 4) for k, v in agg.items()}
+        roof["per_kernel_note"] = ("per_kernel_ms: per-op CUDA events, plain launches (sum > ms_per_step); per_kernel_ms_in_step: the "
+                                   "same shares of the graph-replayed, timed step (sum = ms_per_step)")
         tr, tr_file = load_traffic()
         if tr and top in tr["kernels"] and tr.get("batch") == B:
             t_ = tr["kernels"][top]
@@ -478,7 +603,7 @@ def run_ours(args, rank, local_rank, world):
                           "before it); overlapped: K steps rotating over the compute streams, whole region / K, flushes included",
             "overlapped": None if ms_overlap is None else {"value": world * B / (ms_overlap * 1e-3), "unit": UNIT,
                                                            "ms_per_step": ms_overlap, "streams": n_str},
-            "config": {"workload": f"configs[1]: log-mel frontend + EfficientNet-B0 embedding forward, batch {B} x 1 s @ 16 kHz clips per GPU",
+            "config": {"workload": workload(B),
                        "global_batch": B * world, "clip_samples": 16000, "parallelism": f"dp{world} (clips sharded, no collective)",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)", "chunk": args.chunk, "chunk_late": args.chunk_late,
                        "weights": "random init (Keras initialisers, randomised BN), no checkpoint available offline"},
@@ -500,7 +625,18 @@ def run_ours(args, rank, local_rank, world):
                              "steps_per_embedding_forward": ft_G, "ms_per_step": ms_ft_group / ft_G,
                              "value": world * ft_B * ft_G / (ms_ft_group * 1e-3), "unit": UNIT,
                              "note": "what transfer_learning.fit does: the embedding is frozen, G steps share one forward"},
-                         "collective": "one NCCL all-reduce(sum) of 18 510 fp32 per step" if world > 1 else "none (1 GPU)"},
+                         "collective": "one NCCL all-reduce(sum) of 18 510 fp32 per step" if world > 1 else "none (1 GPU)",
+                         "phase2": {"what": "transfer_learn phase 2 (reference transfer_learning.py:97-112): forward + backward through "
+                                            "block7a + top conv + dense tower + head, Adam; BASELINE config 3 'head + last block'",
+                                    "ms_per_step": ms_ft2, "batch_per_gpu": ft_B, "value": world * ft_B / (ms_ft2 * 1e-3), "unit": UNIT,
+                                    "gradient_floats": int(trainer.flat.numel()),
+                                    "collective": (f"one NCCL all-reduce(sum) of {trainer.flat.numel()} fp32 ({trainer.flat.numel() * 4 / 1e6:.1f} MB) per step"
+                                                   if world > 1 else "none (1 GPU)"),
+                                    "allreduce_alone_ms": ms_ar,
+                                    "allreduce_bus_GBps": (None if not ms_ar else
+                                                           2 * (world - 1) / world * trainer.flat.numel() * 4 / (ms_ar * 1e-3) / 1e9)}},
+            "multi_rank_parity": parity,
+            "other_configs": extra,
             "wall_s_timed_region": wall,
         }
         print(json.dumps(out))

@@ -164,7 +164,8 @@ int kws_head_input_grad(kws_head_t* h, int B, float* d_demb, void* stream);
  * dense tower.  All contractions (forward, data gradient, weight gradient) are kws_gemm_h16 calls; these are the
  * kernels between them.  16-bit tensors are IEEE half; activation gradients carry a static loss scale.
  * --------------------------------------------------------------------------------------------- */
-int kws_train_transpose_h16(const void* d_in, int rows, int cols, void* d_out, void* stream);   /* out[c][r] = in[r][c] */
+/* out[c * ld_out + r] = in[r][c]; ld_out >= rows (the weight-gradient GEMMs contract over the batch, padded to 8) */
+int kws_train_transpose_h16(const void* d_in, int rows, int cols, void* d_out, int ld_out, void* stream);
 int kws_train_swish_fwd(const void* d_z, size_t n, void* d_a, void* stream);
 int kws_train_gap_swish_fwd(const void* d_t, int B, int P, int C, void* d_h0, void* stream);    /* mean_p swish(t) */
 int kws_train_gap_swish_bwd(const void* d_dh0, const void* d_t, int B, int P, int C, void* d_dt, void* stream);

@@ -60,7 +60,7 @@ SIGNATURES = {
     "kws_head_get_params": (c_int, [c_void_p, c_void_p]),
     "kws_head_reset_optimizer": (c_int, [c_void_p]),
     "kws_head_input_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
-    "kws_train_transpose_h16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "kws_train_transpose_h16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "kws_train_swish_fwd": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "kws_train_gap_swish_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "kws_train_gap_swish_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

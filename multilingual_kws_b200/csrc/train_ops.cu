@@ -35,7 +35,7 @@ __device__ __forceinline__ float dswish_x(float x) {
 }
 
 // out[c][r] = in[r][c]
-__global__ void __launch_bounds__(256) transpose_h16_kernel(const uint16_t* __restrict__ in, int rows, int cols,
+__global__ void __launch_bounds__(256) transpose_h16_kernel(const uint16_t* __restrict__ in, int rows, int cols, int ld_out,
                                                             uint16_t* __restrict__ out) {
   __shared__ uint16_t tile[32][34];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) transpose_h16_kernel(const uint16_t* __re
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + tx;
-    if (c < cols && r < rows) out[(size_t)c * rows + r] = tile[tx][i];
+    if (c < cols && r < rows) out[(size_t)c * ld_out + r] = tile[tx][i];
   }
 }
 
@@ -242,10 +242,10 @@ inline int grid_for(size_t n) { const size_t g = (n + kT - 1) / kT; return (int)
 #define ST(s) ((cudaStream_t)(s))
 #define LAUNCH_OK() KWS_CUDA_CHECK(cudaGetLastError()); return KWS_OK
 
-extern "C" int kws_train_transpose_h16(const void* d_in, int rows, int cols, void* d_out, void* stream) {
-  KWS_REQUIRE(d_in && d_out && rows > 0 && cols > 0, "kws_train_transpose_h16: bad argument");
+extern "C" int kws_train_transpose_h16(const void* d_in, int rows, int cols, void* d_out, int ld_out, void* stream) {
+  KWS_REQUIRE(d_in && d_out && rows > 0 && cols > 0 && ld_out >= rows, "kws_train_transpose_h16: bad argument");
   transpose_h16_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, ST(stream)>>>(
-      static_cast<const uint16_t*>(d_in), rows, cols, static_cast<uint16_t*>(d_out));
+      static_cast<const uint16_t*>(d_in), rows, cols, ld_out, static_cast<uint16_t*>(d_out));
   LAUNCH_OK();
 }
 extern "C" int kws_train_swish_fwd(const void* d_z, size_t n, void* d_a, void* stream) {

@@ -124,10 +124,43 @@ def evaluate(model: FewShotModel, ds) -> Dict[str, float]:
     return dict(loss=loss_sum / max(n, 1), accuracy=correct / max(n, 1))
 
 
+class _TrainerView:
+    """What `evaluate` needs of a model, served by a TailTrainer (the fine-tuned tail is not in the frozen model yet)."""
+
+    def __init__(self, trainer):
+        self.trainer = trainer
+
+    def forward_device(self, specs: torch.Tensor) -> torch.Tensor:
+        if specs.dim() == 4:
+            specs = specs[..., 0]
+        return self.trainer.predict_probs(specs.contiguous())
+
+
+def train_step_embedding(trainer, specs: torch.Tensor, labels: torch.Tensor, lr: float):
+    """Phase-2 step on a GLOBAL batch: each rank takes its shard, runs forward + backward through the trainable top of
+    the embedding and the head, all-reduces the flat gradient buffer (TailTrainer.step) and applies Adam."""
+    dist = _dist()
+    if specs.dim() == 4:
+        specs = specs[..., 0]
+    if dist is not None:
+        r, ws = dist.get_rank(), dist.get_world_size()
+        n = specs.shape[0]
+        lo, hi = n * r // ws, n * (r + 1) // ws
+        specs, labels = specs[lo:hi], labels[lo:hi]
+        if hi == lo:
+            raise ValueError("phase-2 fine-tuning needs at least one clip per rank and step")
+    return trainer.step(specs.contiguous(), labels, lr)
+
+
 def fit(model: FewShotModel, train_ds, validation_data, steps_per_epoch: int, epochs: int, lr: float,
-        csvlog_dest=None, verbose=1, group_clips: int = 4096) -> Dict[str, List[float]]:
+        csvlog_dest=None, verbose=1, group_clips: int = 4096, trainer=None) -> Dict[str, List[float]]:
     """Keras-style fit of the head.  Steps are executed in groups that share one embedding forward of about
-    `group_clips` clips (`train_steps_grouped`; group_clips = 0: one forward per step) — same updates, same history."""
+    `group_clips` clips (`train_steps_grouped`; group_clips = 0: one forward per step) — same updates, same history.
+    With `trainer` (a finetune.TailTrainer: phase 2, the top of the embedding trains too) every step is its own
+    forward / backward pass."""
+    if trainer is not None:
+        group_clips = 0
+        model = _TrainerView(trainer)
     history = {"loss": [], "accuracy": [], "val_loss": [], "val_accuracy": []}
     it = iter(train_ds)
     writer = None
@@ -146,7 +179,9 @@ def fit(model: FewShotModel, train_ds, validation_data, steps_per_epoch: int, ep
             while len(group) < min(want, steps_per_epoch - done):
                 specs, labels = next(it)
                 group.append((specs.cuda(), labels.cuda()))
-            for loss, acc in train_steps_grouped(model, group, lr):
+            results = ([train_step_embedding(trainer, *group[0], lr)] if trainer is not None
+                       else train_steps_grouped(model, group, lr))
+            for loss, acc in results:
                 loss_sum += loss
                 acc_sum += acc
             done += len(group)
@@ -212,9 +247,18 @@ def transfer_learn(
     history = fit(xfer, train_ds, val_ds, steps_per_epoch=batch_size * num_batches, epochs=num_epochs, lr=primary_lr,
                   csvlog_dest=csvlog_dest, verbose=verbose)
     if backprop_into_embedding:
-        # The reference's phase 2 un-freezes the whole nested embedding (transfer_learning.py:97-112).
-        # Backward through the EfficientNet stack is not built yet; fail loudly rather than silently skipping it.
-        raise NotImplementedError("backprop_into_embedding=True (full-embedding fine-tune) is not implemented")
+        # Reference phase 2 (transfer_learning.py:97-112): "unfreeze the top 20 layers while leaving BatchNorm layers
+        # frozen", recompile with Adam(embedding_lr) (fresh optimiser state), fit again.  The embedding's last 20 layers
+        # are block7a, top_conv and the dense tower: finetune.TailTrainer (see its docstring for how the reference's
+        # loop over the 3-layer Sequential differs from that stated intent).
+        from ..finetune import TailTrainer
+        xfer.head.reset_optimizer()
+        trainer = TailTrainer(embedding, xfer.head)
+        history = fit(xfer, train_ds, val_ds, steps_per_epoch=batch_size * num_batches, epochs=num_epochs, lr=embedding_lr,
+                      csvlog_dest=csvlog_dest, verbose=verbose, trainer=trainer)
+        tuned = EmbeddingModel(trainer.export_weights(), dtype=embedding.dtype)
+        tuned.trainable = True
+        xfer = FewShotModel(tuned, xfer.head)
 
     va = history["val_accuracy"][-1]
     name = f"xfer_epochs_{num_epochs}_bs_{batch_size}_nbs_{num_batches}_val_acc_{va:0.2f}_target_{target}"

@@ -67,7 +67,8 @@ class _Param:
 
     def refresh_transpose(self):
         if self.w16_t is not None:
-            _lib.check(_lib.lib().kws_train_transpose_h16(self.w16.data_ptr(), self.rows, self.cols, self.w16_t.data_ptr(), _st()))
+            _lib.check(_lib.lib().kws_train_transpose_h16(self.w16.data_ptr(), self.rows, self.cols, self.w16_t.data_ptr(),
+                                                          self.rows, _st()))
 
 
 class TailTrainer:
@@ -147,8 +148,9 @@ class TailTrainer:
     def _tr(self, x: torch.Tensor) -> torch.Tensor:
         """[R, C] fp16 -> [C, R] (the weight-gradient GEMMs contract over the batch, which must be the K-major axis)."""
         r, c = x.shape
-        out = torch.empty((c, r), dtype=torch.float16, device=self.dev)
-        _lib.check(_lib.lib().kws_train_transpose_h16(x.data_ptr(), r, c, out.data_ptr(), _st()))
+        r_pad = (r + 7) & ~7                    # the GEMM wants K % 8 == 0: zero columns add nothing to the sums
+        out = (torch.empty if r_pad == r else torch.zeros)((c, r_pad), dtype=torch.float16, device=self.dev)
+        _lib.check(_lib.lib().kws_train_transpose_h16(x.data_ptr(), r, c, out.data_ptr(), r_pad, _st()))
         return out
 
     def _wgrad(self, dz: torch.Tensor, x: torch.Tensor, p: _Param) -> None:
@@ -277,8 +279,6 @@ class TailTrainer:
         """One optimisation step on the LOCAL shard `feats`/`labels`; the gradients (sums) are all-reduced across the ranks
         of torch.distributed.  Returns (mean loss, accuracy) of the global batch."""
         import torch.distributed as dist
-        if feats.shape[0] % 8:
-            raise ValueError("the per-rank batch must be a multiple of 8 (GEMM K alignment of the weight-gradient GEMMs)")
         self.forward_tail(self.tail_input(feats), keep=True)
         self.backward(labels)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -113,9 +113,18 @@ def test_transfer_learn_end_to_end(world, tmp_path):
     model.save(out)
     again = FewShotModel.load(out)
     assert np.array_equal(again.predict(world["feats"][:7]), preds)
-    with pytest.raises(NotImplementedError):
-        transfer_learning.transfer_learn("tiempo", world["train"], world["val"], world["unk"], 1, 1, 2, 1e-3, True, 1e-4,
-                                         s, world["base"], "dense_2", bg_datadir=world["bg"], verbose=0)
+    # phase 2 (reference transfer_learning.py:97-112): the top 20 layers of the embedding train too, fresh Adam(embedding_lr)
+    before = {k: v.copy() for k, v in model.embedding.weights.items()}
+    name2, model2, details2 = transfer_learning.transfer_learn(
+        "tiempo", world["train"], world["val"], world["unk"], 1, 1, 4, 1e-3, True, 1e-4, s, world["base"], "dense_2",
+        bg_datadir=world["bg"], verbose=0)
+    assert name2.startswith("xfer_epochs_1_bs_4_nbs_1_val_acc_") and model2.head.step_count == 4     # optimiser was reset
+    w2 = model2.embedding.weights
+    changed = [k for k in w2 if not np.array_equal(w2[k], before[k])]
+    assert changed and all(k.startswith(("block7a_", "top_conv", "dense")) and "_bn/" not in k for k in changed), changed
+    assert {"dense_2/kernel", "top_conv/kernel", "block7a_expand_conv/kernel", "block7a_se_reduce/bias"} <= set(changed)
+    p2 = model2.predict(world["feats"][:7, :, :, None])
+    assert p2.shape == (7, 3) and np.allclose(p2.sum(1), 1, atol=1e-5)
 
 
 def test_training_learns_separable_classes(world):
