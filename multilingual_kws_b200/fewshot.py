@@ -121,15 +121,30 @@ class FewShotModel:
         return torch.cat(outs).numpy()
 
     def save(self, path: os.PathLike) -> None:
+        """``model.save(path)`` (reference run.py:300): ``path/variables/variables.{index,data-*}`` in the object-graph layout
+        Keras gives Sequential[embedding, Dense, Dense] (savedmodel.save_keras_model; no saved_model.pb — that is the traced
+        TensorFlow graph) + ``path/weights.npz`` for this package's loader."""
+        from .savedmodel import save_keras_model
         os.makedirs(str(path), exist_ok=True)
         w = dict(self.embedding.weights)
-        for k, v in self.head.params_dict().items():
+        hp = self.head.params_dict()
+        save_keras_model(path, w, head=hp)
+        for k, v in hp.items():
             w["fewshot_head/" + k] = v
         W.save_npz(os.path.join(str(path), "weights.npz"), w)
 
     @classmethod
     def load(cls, path: os.PathLike, **kw) -> "FewShotModel":
+        """Loads ``path/weights.npz`` or, without it, a few-shot Keras SavedModel directory (``variables/variables.index``:
+        the trailing Dense(<=32) -> Dense(<=8) pair becomes the head, savedmodel.split_fewshot_variables)."""
         p = str(path)
+        if os.path.isdir(p) and not os.path.isfile(os.path.join(p, "weights.npz")) and \
+                os.path.isfile(os.path.join(p, "variables", "variables.index")):
+            from .savedmodel import load_keras_variables, split_fewshot_variables
+            w, hp = split_fewshot_variables({k: np.asarray(v) for k, v in load_keras_variables(p).items()})
+            if hp is None:
+                raise ValueError(f"{p}: no few-shot head (Dense -> Dense classifier) in the SavedModel")
+            return cls(EmbeddingModel({k: np.asarray(v, np.float32) for k, v in w.items()}, **kw), Head.from_params(hp))
         if os.path.isdir(p):
             p = os.path.join(p, "weights.npz")
         w = W.load_npz(p)

@@ -85,8 +85,11 @@ class EmbeddingModel:
         p = str(path)
         if os.path.isdir(p) and not os.path.isfile(os.path.join(p, "weights.npz")) and \
                 os.path.isfile(os.path.join(p, "variables", "variables.index")):
-            from .savedmodel import load_keras_variables
-            w = {k: np.asarray(v, np.float32) for k, v in load_keras_variables(p).items()}
+            from .savedmodel import load_keras_variables, split_fewshot_variables
+            # Dense layers are resolved by ORDER (Keras suffixes them per session: dense_7, dense_8 ...); a few-shot
+            # model's trailing head is dropped here (FewShotModel.load keeps it)
+            w, _ = split_fewshot_variables({k: np.asarray(v) for k, v in load_keras_variables(p).items()})
+            w = {k: np.asarray(v, np.float32) for k, v in w.items()}
             return cls(cut_at(w, output_layer), **kw)
         if os.path.isdir(p):
             p = os.path.join(p, "weights.npz")
@@ -96,7 +99,10 @@ class EmbeddingModel:
         return cls(cut_at(W.load_npz(p), output_layer), **kw)
 
     def save(self, path: os.PathLike) -> None:
+        """weights.npz + the variables checkpoint in Keras' object-graph layout (savedmodel.save_keras_model)."""
+        from .savedmodel import save_keras_model
         os.makedirs(str(path), exist_ok=True)
+        save_keras_model(path, self.weights)
         W.save_npz(os.path.join(str(path), "weights.npz"), self.weights)
 
     def __del__(self):

@@ -16,11 +16,23 @@ needed here, so this module reads the checkpoint ("tensor bundle") inside the Sa
   key (``layer_with_weights-3/depthwise_kernel/.ATTRIBUTES/VARIABLE_VALUE``) — which is how ``load_keras_variables``
   returns a Keras-named dict without having to guess the layer order.
 
+EXPORT (`save_keras_model`, used by ``FewShotModel.save`` / ``EmbeddingModel.save`` for the reference's
+``model.save(output)``, run.py:300): writes ``<dir>/variables/variables.{index,data-00000-of-00001}`` as a TF2
+object-based checkpoint whose object graph has the shape Keras gives these models — root -> ``layer_with_weights-i`` ->
+``kernel`` / ``bias`` / ``gamma`` / ... -> ``.ATTRIBUTES/VARIABLE_VALUE``, the few-shot model as
+Sequential[Functional embedding, Dense(18), Dense(3)] with the embedding nested under ``layer_with_weights-0`` — i.e. what
+``tf.keras.Model.load_weights(<dir>/variables/variables)`` / ``tf.train.Checkpoint.restore`` match against a freshly built
+Keras model of the same architecture.  ``saved_model.pb`` (the traced TensorFlow graph + Keras metadata) cannot be produced
+without TensorFlow and is NOT written; ``weights.npz`` is written next to it for this package's own loader.
+
 STATUS: written from the published format descriptions (tensorflow/core/lib/io/table_format.txt, tensor_bundle.proto,
-trackable_object_graph.proto).  No TensorFlow-written file exists in this environment, so the reader has only been
-exercised against files produced by the writer below, which follows the same description (tests/test_savedmodel.py) —
-it is NOT yet validated against a real SavedModel.  Snappy-compressed index blocks (TensorFlow writes the bundle index
-uncompressed) are rejected with a clear error.
+trackable_object_graph.proto).  No TensorFlow-written file exists in this environment.  The reader is tested against (a)
+files produced by the writer below and (b) a fixture assembled by an independent route — tests/golden/make_tf_bundle_fixture.py
+encodes the protos with the google.protobuf runtime from descriptors written out from the .proto definitions, builds the
+table with its own block builder (several data blocks, restart interval 16, prefix-compressed keys, nested object graph,
+a string tensor, a partitioned variable) and its own bitwise CRC-32C — committed under tests/golden/tf_bundle_fixture/.
+It is still NOT validated against a file TensorFlow wrote.  Snappy-compressed index blocks (TensorFlow writes the bundle
+index uncompressed) are rejected with a clear error.
 """
 from __future__ import annotations
 
@@ -418,3 +430,116 @@ def write_keras_checkpoint(model_dir: os.PathLike, variables: Dict[str, np.ndarr
     with open(prefix + ".data-00000-of-00001", "wb") as f:
         f.write(bytes(blob))
     write_table(prefix + ".index", items)
+
+
+# ------------------------------------------------------------------ export in Keras' own object-graph layout
+def _layer_groups(variables: Dict[str, np.ndarray]) -> List[Tuple[str, List[Tuple[str, np.ndarray]]]]:
+    """[(layer name, [(attribute, array)])] in model order: the order of `weights.param_shapes()` (= Keras' layer order
+    for EfficientNetB0 + tower) for known names, then anything else alphabetically."""
+    from . import weights as W
+    order = {}
+    for k in W.param_shapes(tuple(8 for _ in range(8))):     # names only; 8 dense layers cover any tower length
+        order.setdefault(k.rsplit("/", 1)[0], len(order))
+    groups: Dict[str, List[Tuple[str, np.ndarray]]] = {}
+    for k, v in variables.items():
+        if k.startswith(("fewshot_head/", "kws_meta/")):
+            continue
+        layer, attr = k.rsplit("/", 1)
+        groups.setdefault(layer, []).append((attr, np.asarray(v)))
+    return sorted(groups.items(), key=lambda kv: (order.get(kv[0], 10 ** 6), kv[0]))
+
+
+def write_object_checkpoint(prefix: os.PathLike, tree: dict) -> None:
+    """TF2 object-based checkpoint from a nested dict: {child local name: subtree | (full_name, array)}.  Checkpoint keys
+    are the child paths + "/.ATTRIBUTES/VARIABLE_VALUE", the object graph mirrors the tree."""
+    prefix = os.fspath(prefix)
+    os.makedirs(os.path.dirname(prefix), exist_ok=True)
+    blob = bytearray()
+    items: Dict[bytes, bytes] = {b"": _pb_varint(1, 1) + _pb_varint(2, 0) + _pb_bytes(3, _pb_varint(1, 1))}
+    nodes: List[bytes] = []
+
+    def visit(sub, path: str) -> int:
+        nid = len(nodes)
+        nodes.append(b"")
+        if isinstance(sub, dict):
+            body = b""
+            for name, child in sub.items():
+                cid = visit(child, f"{path}/{name}" if path else name)
+                body += _pb_bytes(1, _pb_varint(1, cid) + _pb_bytes(2, name.encode()))
+            nodes[nid] = body
+            return nid
+        full_name, arr = sub
+        arr = np.asarray(arr, order="C")
+        if arr.dtype not in _DTYPE_IDS:
+            raise ValueError(f"{full_name}: dtype {arr.dtype} cannot be written")
+        key = path + "/.ATTRIBUTES/VARIABLE_VALUE"
+        raw = arr.astype(arr.dtype.newbyteorder("<"), copy=False).tobytes()
+        shape = b"".join(_pb_bytes(2, _pb_varint(1, int(d))) for d in arr.shape)
+        items[key.encode()] = (_pb_varint(1, _DTYPE_IDS[arr.dtype]) + _pb_bytes(2, shape) + _pb_varint(4, len(blob)) +
+                               _pb_varint(5, len(raw)) + _pb(6, 5, struct.pack("<I", mask_crc(crc32c(raw)))))
+        blob.extend(raw)
+        nodes[nid] = _pb_bytes(2, _pb_bytes(1, b"VARIABLE_VALUE") + _pb_bytes(2, full_name.encode()) + _pb_bytes(3, key.encode()))
+        return nid
+
+    visit(tree, "")
+    graph = b"".join(_pb_bytes(1, nd) for nd in nodes)
+    lengths = _write_varint(len(graph))
+    raw = lengths + struct.pack("<I", mask_crc(crc32c(lengths))) + graph
+    items[OBJECT_GRAPH_KEY.encode()] = (_pb_varint(1, _DT_STRING) + _pb_bytes(2, b"") + _pb_varint(4, len(blob)) +
+                                       _pb_varint(5, len(raw)) + _pb(6, 5, struct.pack("<I", mask_crc(crc32c(raw)))))
+    blob.extend(raw)
+    with open(prefix + ".data-00000-of-00001", "wb") as f:
+        f.write(bytes(blob))
+    write_table(prefix + ".index", items)
+
+
+def keras_tree(variables: Dict[str, np.ndarray]) -> dict:
+    """Object tree of a Keras functional model: layer_with_weights-i -> attribute -> (full name, array)."""
+    tree = {}
+    for i, (layer, attrs) in enumerate(_layer_groups(variables)):
+        tree[f"layer_with_weights-{i}"] = {attr: (f"{layer}/{attr}", arr) for attr, arr in attrs}
+    return tree
+
+
+def save_keras_model(model_dir: os.PathLike, variables: Dict[str, np.ndarray], head: Optional[Dict[str, np.ndarray]] = None) -> None:
+    """``model.save(model_dir)`` without TensorFlow: the variables checkpoint of the embedding (functional model) or, with
+    `head` = {w1, b1, w2, b2}, of the few-shot Sequential[embedding, Dense(hidden, tanh), Dense(classes, softmax)] the
+    reference builds (transfer_learning.py:47-53), whose new Dense layers Keras names after the tower's (dense_3, dense_4)."""
+    emb = keras_tree(variables)
+    if head is None:
+        tree = emb
+    else:
+        n_dense = len({k.rsplit("/", 1)[0] for k in variables if k.startswith("dense")})
+        names = [f"dense_{n_dense}", f"dense_{n_dense + 1}"]
+        tree = {"layer_with_weights-0": emb,
+                "layer_with_weights-1": {"kernel": (names[0] + "/kernel", np.asarray(head["w1"], np.float32)),
+                                         "bias": (names[0] + "/bias", np.asarray(head["b1"], np.float32))},
+                "layer_with_weights-2": {"kernel": (names[1] + "/kernel", np.asarray(head["w2"], np.float32)),
+                                         "bias": (names[1] + "/bias", np.asarray(head["b2"], np.float32))}}
+    write_object_checkpoint(os.path.join(os.fspath(model_dir), "variables", "variables"), tree)
+
+
+def _dense_index(layer: str) -> int:
+    tail = layer.rsplit("_", 1)[-1]
+    return int(tail) if tail.isdigit() else 0
+
+
+def split_fewshot_variables(variables: Dict[str, np.ndarray]) -> Tuple[Dict[str, np.ndarray], Optional[Dict[str, np.ndarray]]]:
+    """Separates a few-shot SavedModel's variables into (embedding variables, head or None).  Dense layers are taken in
+    index order whatever their suffix (Keras numbers layers per session: ``dense_3``, ``dense_17`` ...): the tower is
+    renamed to ``dense``, ``dense_1``, ...; if the last two Dense layers look like the reference's head (hidden <= 32
+    units feeding <= 8 classes, transfer_learning.py:47-53) they become {w1, b1, w2, b2}."""
+    dense = sorted({k.rsplit("/", 1)[0] for k in variables if k.split("/")[0].startswith("dense") and k.endswith("/kernel")},
+                   key=_dense_index)
+    out = {k: v for k, v in variables.items() if not k.split("/")[0].startswith("dense")}
+    head = None
+    if len(dense) >= 3:
+        k1, k2 = variables[dense[-2] + "/kernel"], variables[dense[-1] + "/kernel"]
+        if k1.ndim == 2 and k2.ndim == 2 and k1.shape[1] == k2.shape[0] and k1.shape[1] <= 32 and k2.shape[1] <= 8:
+            head = dict(w1=k1, b1=variables[dense[-2] + "/bias"], w2=k2, b2=variables[dense[-1] + "/bias"])
+            dense = dense[:-2]
+    for i, layer in enumerate(dense):
+        new = "dense" if i == 0 else f"dense_{i}"
+        out[new + "/kernel"] = variables[layer + "/kernel"]
+        out[new + "/bias"] = variables[layer + "/bias"]
+    return out, head

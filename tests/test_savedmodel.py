@@ -74,3 +74,59 @@ def test_keras_checkpoint_round_trip(tmp_path):
     data.write_bytes(bytes(raw))
     with pytest.raises(ValueError, match="checksum"):
         SM.load_keras_variables(tmp_path / "small", verify_data_crc=True)
+
+
+FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_bundle_fixture")
+
+
+def test_reader_against_independently_built_bundle():
+    """tests/golden/tf_bundle_fixture was assembled by tests/golden/make_tf_bundle_fixture.py WITHOUT this package's
+    writer: protos encoded by the google.protobuf runtime, its own multi-block table builder (prefix compression, restart
+    interval 16, shortened index separators), a bitwise CRC-32C, two data shards, a nested Keras object graph."""
+    import json
+    meta = json.load(open(os.path.join(FIX, "expected.json")))
+    assert meta["data_blocks"] >= 4                                    # really a multi-block index
+    with np.load(os.path.join(FIX, "expected.npz")) as z:
+        want = {k.replace("__", "/"): z[k] for k in z.files}
+    prefix = os.path.join(FIX, "plain", "variables")
+    table = SM.read_table(prefix + ".index")                          # block checksums verified
+    assert len(table) == meta["n_entries"]
+    raw = SM.load_checkpoint(prefix, verify_data_crc=True)
+    assert np.array_equal(raw["extras/half"], want["extras/half"]) and raw["extras/half"].dtype == np.float16
+    assert np.array_equal(raw["extras/bf16"], want["extras/bf16"])
+    assert [x.decode() for x in raw["extras/labels"]] == meta["labels"]
+    got = SM.load_keras_variables(prefix, verify_data_crc=True)
+    assert sorted(got) == meta["keras_names"]                          # optimizer slots / iter skipped, Keras names kept
+    for k in got:
+        assert got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), k
+    assert got["normalization/count"].dtype == np.int64 and int(got["normalization/count"]) == 12345
+    # a few-shot SavedModel with session-suffixed Dense names: tower by order, trailing Dense(18) -> Dense(3) = the head
+    emb, head = SM.split_fewshot_variables(got)
+    assert sorted(k for k in emb if k.startswith("dense")) == ["dense/bias", "dense/kernel", "dense_1/bias", "dense_1/kernel",
+                                                             "dense_2/bias", "dense_2/kernel"]
+    assert np.array_equal(emb["dense/kernel"], want["dense_7/kernel"]) and np.array_equal(emb["dense_2/bias"], want["dense_9/bias"])
+    assert head is not None and head["w1"].shape == (4, 18) and np.array_equal(head["w2"], want["dense_11/kernel"])
+    with pytest.raises(ValueError, match="partitioned/embeddings"):
+        SM.load_checkpoint(os.path.join(FIX, "sliced", "variables"))
+
+
+def test_export_in_keras_object_graph_layout(tmp_path):
+    """model.save (reference run.py:300): checkpoint keys follow Keras' object graph, few-shot model = Sequential[embedding,
+    Dense, Dense]; read back by the loader, head recovered, tower names by order."""
+    full = W.random_init(0, randomize_bn=True, dense_units=(32, 32, 16))
+    w = {k: v for k, v in full.items() if k.startswith(("normalization", "stem", "block1a", "top_", "dense"))}
+    head = dict(w1=np.full((16, 18), 0.5, np.float32), b1=np.arange(18, dtype=np.float32),
+                w2=np.full((18, 3), -1.0, np.float32), b2=np.zeros(3, np.float32))
+    SM.save_keras_model(tmp_path / "m", w, head)
+    keys = sorted(k.decode() for k in SM.read_table(tmp_path / "m" / "variables" / "variables.index"))
+    assert "layer_with_weights-0/layer_with_weights-0/mean/.ATTRIBUTES/VARIABLE_VALUE" in keys           # Normalization first
+    assert "layer_with_weights-0/layer_with_weights-1/kernel/.ATTRIBUTES/VARIABLE_VALUE" in keys        # stem_conv
+    assert "layer_with_weights-1/kernel/.ATTRIBUTES/VARIABLE_VALUE" in keys and "layer_with_weights-2/bias/.ATTRIBUTES/VARIABLE_VALUE" in keys
+    got = SM.load_keras_variables(tmp_path / "m", verify_data_crc=True)
+    assert "dense_3/kernel" in got and "dense_4/bias" in got                                            # Keras' names of the new layers
+    emb, hp = SM.split_fewshot_variables(got)
+    assert set(emb) == set(w) and all(np.array_equal(emb[k], w[k]) for k in w)
+    assert all(np.array_equal(hp[k], head[k]) for k in head)
+    SM.save_keras_model(tmp_path / "e", w)                                                              # embedding alone
+    emb2, hp2 = SM.split_fewshot_variables(SM.load_keras_variables(tmp_path / "e"))
+    assert hp2 is None and set(emb2) == set(w)
