@@ -514,6 +514,78 @@ def run_ours(args, rank, local_rank, world):
             extra["config5_streaming_30min"] = rowsx
             del audio_d
 
+    # ---- fine-tuning END TO END through the public API (dataset from WAV files, device augmentation, frontend, embedding,
+    # head): transfer_learn() at the reference's defaults (run.py:219-223: 4 epochs x 64 steps x batch 64 = 16 384 augmented
+    # clips) and fit() at BASELINE config 3's shape (batch 512 x 100 steps), wall clock
+    ft_e2e = None
+    if rank == 0 and world == 1 and not args.no_finetune_e2e:
+        import shutil
+        import tempfile
+        from multilingual_kws_b200.embedding import input_data, transfer_learning
+        tmp = tempfile.mkdtemp(prefix="kws_ft_")
+        try:
+            rng_ = np.random.default_rng(0)
+            clips = synthetic_pcm(96, cfg_id=11).astype(np.float64) / 32768.0
+
+            def wavs(sub, idx):
+                os.makedirs(os.path.join(tmp, sub), exist_ok=True)
+                out_ = []
+                for i in idx:
+                    p_ = os.path.join(tmp, sub, f"clip{i}.wav")
+                    input_data.encode_wav(p_, clips[i])
+                    out_.append(p_)
+                return out_
+            train_f, val_f, unk_f = wavs("kw", range(0, 5)), wavs("kw_val", range(5, 21)), wavs("other", range(21, 96))
+            os.makedirs(os.path.join(tmp, "_background_noise_"))
+            input_data.encode_wav(os.path.join(tmp, "_background_noise_", "noise.wav"), rng_.normal(0, 0.05, 16000 * 60))
+            os.makedirs(os.path.join(tmp, "base"))
+            W.save_npz(os.path.join(tmp, "base", "weights.npz"), weights)
+            settings_ = input_data.standard_microspeech_model_settings(3)
+            kw = dict(target="kw", train_files=train_f, val_files=val_f, unknown_files=unk_f, num_epochs=4, num_batches=1,
+                      batch_size=64, primary_lr=1e-3, backprop_into_embedding=False, embedding_lr=0, model_settings=settings_,
+                      base_model_path=os.path.join(tmp, "base"), base_model_output="dense_2", UNKNOWN_PERCENTAGE=50.0,
+                      bg_datadir=os.path.join(tmp, "_background_noise_") + "/", verbose=0)
+            transfer_learning.transfer_learn(**dict(kw, num_epochs=1))           # warm-up: library load, graphs, allocator
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, m_, det_ = transfer_learning.transfer_learn(**kw)
+            torch.cuda.synchronize()
+            wall_tl = time.perf_counter() - t0
+            # config 3 shape through the same dataset pipeline: batch 512, 100 steps (fit on a prepared model)
+            ds = input_data.AudioDataset(model_settings=settings_, commands=["kw"], background_data_dir=kw["bg_datadir"],
+                                         unknown_files=unk_f, unknown_percentage=50.0,
+                                         spec_aug_params=input_data.SpecAugParams(percentage=80), seed=1, device_augment="batched")
+            tr_ds = ds.init_single_target(-1, train_f, is_training=True).shuffle(buffer_size=1000).repeat().batch(512)
+            va_ds = ds.init_single_target(-1, val_f, is_training=False).batch(512)
+            transfer_learning.fit(m_, tr_ds, va_ds, steps_per_epoch=8, epochs=1, lr=1e-3, verbose=0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            transfer_learning.fit(m_, tr_ds, va_ds, steps_per_epoch=100, epochs=1, lr=1e-3, verbose=0)
+            torch.cuda.synchronize()
+            wall_c3 = time.perf_counter() - t0
+            # the dataset pipeline alone (element generation on the host + augmentation kernel + frontend), no model
+            it_ = iter(tr_ds)
+            next(it_)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                next(it_)
+            torch.cuda.synchronize()
+            wall_ds = (time.perf_counter() - t0) / 20
+            ft_e2e = {
+                "transfer_learn_reference_defaults": {"epochs": 4, "steps": 256, "batch": 64, "clips": 16384, "wall_s": wall_tl,
+                                                       "utt_per_s": 16384 / wall_tl, "val_accuracy": det_["val_accuracy"],
+                                                       "includes": "model load from disk, WAV decode, dataset, device augmentation, frontend, "
+                                                                   "embedding, head steps, validation pass per epoch"},
+                "config3_batch512_x100_steps": {"wall_s": wall_c3, "ms_per_step": wall_c3 * 10, "utt_per_s": 51200 / wall_c3,
+                                                "dataset_pipeline_alone_ms_per_batch": wall_ds * 1e3,
+                                                "device_only_ms_per_step": None if ms_ft_group is None else ms_ft_group / ft_G,
+                                                "note": "fit() over AudioDataset batches (vectorised decision draws -> plan items -> kws_augment_pcm -> "
+                                                        "frontend -> grouped embedding forward -> head steps); device_only = finetune.grouped"},
+            }
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
     # ---- per-kernel shares (CUDA events around every launch, on the launch stream) -> roofline of the dominant kernel
     peaks = load_peaks()
     roof, shares = None, None
@@ -660,6 +732,7 @@ def run_ours(args, rank, local_rank, world):
                                     "allreduce_alone_ms": ms_ar,
                                     "allreduce_bus_GBps": (None if not ms_ar else
                                                            2 * (world - 1) / world * trainer.flat.numel() * 4 / (ms_ar * 1e-3) / 1e9)}},
+            "finetune_e2e": ft_e2e,
             "multi_rank_parity": parity,
             "other_configs": extra,
             "wall_s_timed_region": wall,
@@ -684,6 +757,7 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=120.0,
                     help="wall-clock budget of the whole --impl reference run (the per-step sample is sized to fit)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-finetune-e2e", action="store_true", help="skip the transfer_learn() end-to-end timing")
     ap.add_argument("--pipe-streams", type=int, default=3, help="compute streams the host pipeline / overlapped figure rotate over")
     ap.add_argument("--sm-budget", default="", help="head,tail SM budget of the throughput schedule (default: the pipeline's)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying the CUDA graph")

@@ -540,9 +540,9 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
       names.push_back(nm);
     }
     if (names.empty()) { B.err = "no dense layers in the weight container"; return fail(KWS_ERR_ARG); }
-    // "kws_meta/dense_cut": the tower was cut before its own last layer (model.cut_at): the output is then that layer's
-    // ReLU, as base_model.get_layer(name).output is in the reference; the SELU belongs to the original last layer only
-    const bool cut_before_last = wm.find("kws_meta/dense_cut") != wm.end();
+    // Each Dense layer keeps ITS OWN activation wherever the tower is cut (base_model.get_layer(name).output in the
+    // reference, transfer_learning.py:38-43): the models of train_*_embedding.py:81-100 have relu, relu, selu and then the
+    // linear classifier layer, so dense / dense_1 -> ReLU, dense_2 -> SELU, anything after it -> none.
     for (size_t i = 0; i < names.size(); ++i) {
       const HostTensor& kt = wm[names[i] + "/kernel"];
       if (kt.dims.size() != 2 || (int)kt.dims[0] != fan) { B.err = "bad shape for " + names[i]; return fail(KWS_ERR_ARG); }
@@ -552,7 +552,7 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
       const bool last = i + 1 == names.size();
       Op op;
       op.kind = kOpGemm; op.name = names[i]; op.in_buf = in_buf; op.out_buf = last ? -1 : (in_buf == 1 ? 2 : 1);
-      op.rows_per_clip = 1; op.N = units; op.K = fan; op.act = (last && !cut_before_last) ? kActSelu : kActRelu;
+      op.rows_per_clip = 1; op.N = units; op.K = fan; op.act = i < 2 ? kActRelu : (i == 2 ? kActSelu : kActNone);
       op.out_f32 = last ? 1 : 0;
       op.w = B.gemm_weight(names[i] + "/kernel", fan, units, nullptr);
       op.bias = B.vec(std::vector<float>(bt->data, bt->data + units));

@@ -236,7 +236,8 @@ def transfer_learn(
         unknown_percentage=UNKNOWN_PERCENTAGE,
         spec_aug_params=input_data.SpecAugParams(percentage=80),
         seed=seed,
-        device_augment=True,      # clips decoded once into a device bank; shift / mix / masks run on the GPU
+        device_augment="batched",  # clips decoded once into a device bank; shift / mix / masks run on the GPU, the
+                                   # decisions of a whole batch are drawn at once (input_data._Dataset._fast_batches)
     )
     init_train_ds = audio_dataset.init_single_target(AUTOTUNE, train_files, is_training=True)
     init_val_ds = audio_dataset.init_single_target(AUTOTUNE, val_files, is_training=False)

@@ -98,8 +98,8 @@ class TailTrainer:
         self.P = self.H * self.W
         dense = [n for n in ("dense", "dense_1", "dense_2", "dense_3") if n + "/kernel" in w]
         self.dense_names = dense
-        if "kws_meta/dense_cut" in w:
-            raise ValueError("fine-tuning expects the tower cut at its own last (SELU) layer")
+        if dense != ["dense", "dense_1", "dense_2"]:
+            raise ValueError("fine-tuning expects the embedding cut at dense_2 (relu, relu, selu tower)")
         sc_e, self.sh_e = _bn_fold(w, f"{block}_expand_bn")
         sc_d, self.sh_d = _bn_fold(w, f"{block}_bn")
         sc_p, self.sh_p = _bn_fold(w, f"{block}_project_bn")

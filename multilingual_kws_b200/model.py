@@ -38,13 +38,8 @@ def cut_at(w: Dict[str, np.ndarray], output_layer: str) -> Dict[str, np.ndarray]
     if output_layer not in names:
         raise ValueError(f"No such layer: {output_layer}. Existing dense layers are: {names}")
     keep = set(names[:names.index(output_layer) + 1])
-    out = {k: v for k, v in w.items()
-           if not k.startswith("fewshot_head/") and (not k.startswith("dense") or k.split("/")[0] in keep)}
-    if output_layer != names[-1]:
-        # the SELU belongs to the tower's own last layer; an earlier cut ends in that layer's ReLU, exactly what
-        # base_model.get_layer(name).output is in the reference (transfer_learning.py:38-43)
-        out["kws_meta/dense_cut"] = np.ones((1,), np.float32)
-    return out
+    return {k: v for k, v in w.items()
+            if not k.startswith("fewshot_head/") and (not k.startswith("dense") or k.split("/")[0] in keep)}
 
 
 class EmbeddingModel:

@@ -139,3 +139,50 @@ def test_dataset_device_path_equals_host_path(kws_lib, tmp_path):
         assert np.array_equal(xh, xd)
         labels_seen |= set(yh.tolist())
     assert labels_seen == {0, 1, 2}                              # silence, unknown and target branches all exercised
+
+
+def test_batched_training_path_statistics(kws_lib, tmp_path):
+    """device_augment="batched" (what transfer_learn uses): whole-batch decision draws.  Same policy as `augment`
+    (reference input_data.py:275-304): branch frequencies, label / mode consistency, masks, determinism per seed."""
+    from multilingual_kws_b200.embedding import input_data
+    pcm = synthetic_pcm(30, cfg_id=13)
+    rng = np.random.default_rng(1)
+
+    def wavs(sub, idx):
+        d = tmp_path / sub
+        d.mkdir()
+        out = []
+        for i in idx:
+            input_data.encode_wav(str(d / f"c{i}.wav"), pcm[i].astype(np.float64) / 32768.0)
+            out.append(str(d / f"c{i}.wav"))
+        return out
+
+    train, unk = wavs("hola", range(5)), wavs("other", range(11, 30))
+    bgd = tmp_path / "_background_noise_"
+    bgd.mkdir()
+    input_data.encode_wav(str(bgd / "a.wav"), rng.normal(0, 0.05, 40000))
+    input_data.encode_wav(str(bgd / "b.wav"), rng.normal(0, 0.2, 17000))
+    s = input_data.standard_microspeech_model_settings(3)
+
+    def batches(seed, n):
+        ds = input_data.AudioDataset(s, ["hola"], str(bgd), unk, unknown_percentage=40.0, silence_percentage=20.0, seed=seed,
+                                     spec_aug_params=input_data.SpecAugParams(percentage=80), device_augment="batched")
+        tr = ds.init_single_target(-1, train, is_training=True).shuffle(1000).repeat().batch(512)
+        assert tr.fast is not None
+        it = iter(tr)
+        return [next(it) for _ in range(n)]
+
+    got = batches(5, 8)
+    x = torch.cat([b[0] for b in got]).cpu().numpy()
+    y = torch.cat([b[1] for b in got]).numpy()
+    assert x.shape == (4096, 49, 40, 1) and y.dtype == np.int64 and np.isfinite(x).all()
+    frac = np.bincount(y, minlength=3) / y.size                  # [silence, unknown, target]
+    assert abs(frac[0] - 0.20) < 0.03 and abs(frac[1] - 0.8 * 0.4) < 0.03 and abs(frac[2] - 0.8 * 0.6) < 0.03, frac
+    # spec-augment: ~80 % of the clips get a mask draw; a masked column / row is exactly zero
+    zero_cols = (np.abs(x[..., 0]).sum(axis=1) == 0).any(axis=1)
+    zero_rows = (np.abs(x[..., 0]).sum(axis=2) == 0).any(axis=1)
+    assert 0.3 < zero_cols.mean() < 0.8 and 0.3 < zero_rows.mean() < 0.9
+    again = batches(5, 2)
+    assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(got[:2], again))     # same seed -> same batches
+    other = batches(6, 1)
+    assert not torch.equal(other[0][1], got[0][1])

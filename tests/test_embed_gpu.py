@@ -101,8 +101,61 @@ def test_bf16_mode_and_chaotic_net_bounds(kws_lib, setup, feats):
     want_c = EO.forward(wc, feats).numpy()
     cos_chaotic = EO.cosine(EmbeddingModel(wc).predict(feats), want_c).min()
     print(f"bf16 on the trained-like net: min cosine {cos_bf16:.5f}; fp16 on the chaotic net: {cos_chaotic:.5f}")
-    assert cos_bf16 >= 0.98
-    assert cos_chaotic >= 0.98
+    assert cos_bf16 >= 0.99
+    # Undamped random initialisation is chaotic: tests/test_precision_budget.py shows on the CPU that rounding ONLY the
+    # weights to fp16 (all arithmetic and activations fp32) already lands at 0.9989 there — no 16-bit-operand tensor-core
+    # path can meet 0.999 on it; the regimes that matter are the trained-like one above and the trained one below.
+    assert cos_chaotic >= 0.995
+
+
+def test_fused_tail_schedules_agree(setup, feats):
+    """kws_embed_set_fuse: the tail (blocks 4a..7a + top conv) as one tcgen05 launch per MBConv block (1) or per run of
+    blocks (2) against the layer-wise schedule (0) and the oracle: block outputs, embedding, ragged batches."""
+    model, _, want, taps = setup
+    x = torch.from_numpy(feats).cuda()
+    base = model.forward_device(x).cpu().numpy()
+    names = model.op_names()
+    try:
+        for mode in (1, 2):
+            model.set_fuse(mode)
+            assert model.launches(feats.shape[0]) < 40
+            got = model.forward_device(x).cpu().numpy()
+            assert np.isfinite(got).all()
+            assert EO.cosine(got, want).min() >= 0.999 and rel_err(got, base) < 0.01, mode
+            for b in (1, 3, 33):
+                assert torch.equal(model.forward_device(x[:b]).cpu(), torch.from_numpy(got[:b])), (mode, b)
+        model.set_fuse(1)                      # every fused block is a launch whose output can be tapped
+        for i, (name, elems) in enumerate(names):
+            if name.endswith("_out") and name[5] in "4567":
+                _, tap = model.forward_device(x, tap_op=i)
+                assert rel_err(tap.float().cpu().numpy(), taps[name].reshape(feats.shape[0], -1)) < 0.02, name
+        model.set_fuse(2)
+        i = [n for n, _ in names].index("top_gap")
+        _, tap = model.forward_device(x, tap_op=i)
+        assert rel_err(tap.float().cpu().numpy(), taps["top_gap"].reshape(feats.shape[0], -1)) < 0.02
+    finally:
+        model.set_fuse(0)
+
+
+def test_trained_weight_regime(kws_lib, feats):
+    """Third weight regime: the torch restatement TRAINED for 150 Adam steps (BatchNorm in training mode) on a synthetic
+    4-way task from plain Keras initialisation (no damping, no calibration) — oracle/effnet_train_oracle.py.  The
+    tolerance north_star states (cosine >= 0.999) has to hold on trained weights."""
+    from multilingual_kws_b200.model import EmbeddingModel
+    from oracle import effnet_train_oracle as TR
+    train_feats = FrontendOracle().features(synthetic_pcm(256, cfg_id=7), threads=4)
+    labels = np.arange(256) % 4                                 # the four clip kinds of the synthetic generator
+    w = TR.train(W.random_init(21), train_feats, labels, steps=150, batch=32, lr=1e-3, seed=1, log=print)
+    # 150 steps at Keras' BN momentum 0.99 leave the moving statistics 22 % of the way at their initial values (the
+    # inference-mode network then collapses to a constant): re-estimate them over the training set, the usual last step
+    EO.forward(w, train_feats, calibrate_bn=True)
+    want = EO.forward(w, feats).numpy()
+    got = EmbeddingModel(w).predict(feats)
+    cos = EO.cosine(got, want)
+    print(f"trained regime: min cosine {cos.min():.6f} rel err {rel_err(got, want):.5f} "
+          f"(cosine between two clips {EO.cosine(want[0], want[1]):.3f})")
+    assert EO.cosine(want[0], want[1]) < 0.99                   # not collapsed
+    assert cos.min() >= 0.999
 
 
 def test_monolingual_head_sizes(kws_lib, feats):
