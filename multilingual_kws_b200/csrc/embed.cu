@@ -152,7 +152,7 @@ struct kws_embed {
   std::vector<FusedBlock> fblocks;
   std::vector<FusedBlockInfo> finfos;  // fblocks[i].info, contiguous (the launcher takes an array)
   FusedBlockDev* d_fblocks = nullptr;  // device array, same order as fblocks (+ the top-conv pseudo-block at the end)
-  std::vector<FusedSegment> segs[3];   // per fuse mode
+  std::vector<FusedSegment> segs[4];   // per fuse mode
 };
 
 namespace {
@@ -259,23 +259,32 @@ static int build_fused_plan(kws_embed* m) {
     sg.blk_lo = i; sg.nblocks = 1; sg.op_lo = fb.op_lo; sg.op_hi = fb.op_hi; sg.in_place = fb.info.residual;
     m->segs[1].push_back(sg);
   }
-  // mode 2: greedy runs.  A run keeps growing while the merged launch still fits at least kMinGroup clips per CTA.
+  // modes 2 and 3: greedy runs.  A run keeps growing while the merged launch still fits at least kMinGroup clips per CTA.
+  // Mode 3 fuses only the blocks with <= 672 expanded channels (4a .. 6a: 12 pixels per clip, where one fused launch beats
+  // the six layer-wise ones); the 1152-channel blocks on 2x2 maps (6b .. 7a) are issue-bound in the fused kernel (their
+  // MMAs have N = 28 rows and cost the same ~148 cycles as N = 256) and stay layer-wise.
   const int kMinGroup = 7;
   m->finfos.resize(n);
   for (int i = 0; i < n; ++i) m->finfos[i] = m->fblocks[i].info;
   const std::vector<FusedBlockInfo>& infos = m->finfos;
-  for (int i = 0; i < n;) {
-    if (!m->fblocks[i].fusable || m->fblocks[i].info.pool_out) { ++i; continue; }
-    int cnt = 1;
-    while (i + cnt < n && m->fblocks[i + cnt].fusable && m->fblocks[i + cnt].op_lo == m->fblocks[i + cnt - 1].op_hi + 1 &&
-           fused_max_group(&infos[i], cnt + 1, m->max_smem) >= kMinGroup)
-      ++cnt;
-    FusedSegment sg;
-    sg.blk_lo = i; sg.nblocks = cnt; sg.op_lo = m->fblocks[i].op_lo; sg.op_hi = m->fblocks[i + cnt - 1].op_hi;
-    sg.in_place = 1;
-    for (int q = 0; q < cnt; ++q) if (!m->fblocks[i + q].info.residual) sg.in_place = 0;
-    m->segs[2].push_back(sg);
-    i += cnt;
+  for (int mode = 2; mode <= 3; ++mode) {
+    auto ok = [&](int i) {
+      const FusedBlock& fb = m->fblocks[i];
+      return fb.fusable && (mode == 2 || (!fb.info.pool_out && fb.info.cexp <= 672));
+    };
+    for (int i = 0; i < n;) {
+      if (!ok(i) || m->fblocks[i].info.pool_out) { ++i; continue; }
+      int cnt = 1;
+      while (i + cnt < n && ok(i + cnt) && m->fblocks[i + cnt].op_lo == m->fblocks[i + cnt - 1].op_hi + 1 &&
+             fused_max_group(&infos[i], cnt + 1, m->max_smem) >= kMinGroup)
+        ++cnt;
+      FusedSegment sg;
+      sg.blk_lo = i; sg.nblocks = cnt; sg.op_lo = m->fblocks[i].op_lo; sg.op_hi = m->fblocks[i + cnt - 1].op_hi;
+      sg.in_place = 1;
+      for (int q = 0; q < cnt; ++q) if (!m->fblocks[i + q].info.residual) sg.in_place = 0;
+      m->segs[mode].push_back(sg);
+      i += cnt;
+    }
   }
   return KWS_OK;
 }
@@ -609,7 +618,7 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
   for (size_t i = 0; i < m->ops.size(); ++i)
     if (m->ops[i].name == "block3b_out") m->tail_op = (int)i + 1;
   m->flops_per_clip = 2.0 * macs;
-  if (const char* env = getenv("KWS_FUSE")) m->fuse = atoi(env) < 0 ? 0 : (atoi(env) > 2 ? 2 : atoi(env));
+  if (const char* env = getenv("KWS_FUSE")) m->fuse = atoi(env) < 0 ? 0 : (atoi(env) > 3 ? 3 : atoi(env));
   {
     const int rc = build_fused_plan(m);
     if (rc != KWS_OK) {
@@ -693,7 +702,7 @@ extern "C" int kws_embed_launches(const kws_embed_t* m, int batch) {
 
 // 0: layer-by-layer schedule; 1: one fused launch per MBConv block of the tail; 2 (default): runs of blocks per launch
 extern "C" int kws_embed_set_fuse(kws_embed_t* m, int mode) {
-  KWS_REQUIRE(m != nullptr && mode >= 0 && mode <= 2, "kws_embed_set_fuse: bad argument");
+  KWS_REQUIRE(m != nullptr && mode >= 0 && mode <= 3, "kws_embed_set_fuse: bad argument");
   m->fuse = mode;
   return KWS_OK;
 }
@@ -733,7 +742,7 @@ static int embed_forward_impl(kws_embed_t* m, const float* d_feats, int batch, f
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (m->use_graph && tap_op < 0 && !host_op_ms && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
       cap == cudaStreamCaptureStatusNone) {
-    const long long sched_key = ((((long long)m->chunk * 100003 + m->chunk_late) * 1024 + sm_head) * 1024 + sm_tail) * 4 + m->fuse;
+    const long long sched_key = ((((long long)m->chunk * 100003 + m->chunk_late) * 1024 + sm_head) * 1024 + sm_tail) * 8 + m->fuse;
     for (auto& g : m->graphs)
       if (g.feats == d_feats && g.emb == d_emb && g.ws == d_workspace && g.batch == batch && g.chunk == sched_key) {
         KWS_CUDA_CHECK(cudaGraphLaunch(g.exec, st));

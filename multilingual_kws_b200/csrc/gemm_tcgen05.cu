@@ -388,7 +388,13 @@ int gemm_h16(const void* a, const void* w, int M, int N, int K, int block_n, con
   // with half the shared memory and 256 TMEM columns (one accumulator stage when block_n > 128).
   const int tiles_total = sh.m_tiles * sh.n_tiles;
   const bool many_tiles = tiles_total >= 2 * sm_count;
-  const size_t budget = ((num_kb <= 2 && sh.block_n <= 128) || (many_tiles && num_kb <= 4)) ? 110 * 1024 : 220 * 1024;
+  // One-tile-per-CTA launches (the whole tail of the network: <= 148 tiles) are latency chains, not bandwidth problems:
+  // with at most half of the SM's shared memory (and <= 256 TMEM columns) the NEXT kernel's CTA fits beside this one, so
+  // its set-up (barriers, TMEM allocation, bias staging, tensor-map fetch) overlaps this kernel under programmatic
+  // dependent launch instead of starting when this CTA exits.  KWS_GEMM_BIG_SMEM=1 restores the old rule (A/B).
+  static const bool big_smem = [] { const char* e = getenv("KWS_GEMM_BIG_SMEM"); return e && atoi(e); }();
+  const bool one_tile = !big_smem && tiles_total <= sm_count && sh.block_n <= 128;
+  const size_t budget = ((num_kb <= 2 && sh.block_n <= 128) || (many_tiles && num_kb <= 4) || one_tile) ? 110 * 1024 : 220 * 1024;
   sh.acc_stages = 2;
   int stages = kGemmMaxStages;
   while (stages > 2 && smem_layout(sh.block_n, sh.block_k, stages, N).total + 1024 > budget) --stages;

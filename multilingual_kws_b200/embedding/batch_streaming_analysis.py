@@ -97,6 +97,29 @@ def stream_inferences(model, model_settings, audio: np.ndarray, sample_rate: int
     return probs if keep_on_device else probs.cpu().numpy()
 
 
+def reference_chunk_rows(n_samples: int, sample_rate: int, clip_samples: int, stride_samples: int, max_chunk_length_sec: int):
+    """Row layout of the `inferences` matrix the REFERENCE returns for a wav of n_samples
+    (batch_streaming_analysis.py:72-123).  Its chunk branch is inverted: for audio of at least max_chunk_length_sec the first
+    "chunk" is the whole signal and every later offset k * max_chunk contributes audio[offset : offset + max_chunk]
+    again, so the saved matrix is the W window rows followed by the windows of those tails.  Returns [(sample offset,
+    number of windows)] per chunk; the first entry is always (0, W).  Only the first W rows are ever read back
+    (the post-processing loop indexes by window, :131-140)."""
+    max_chunk = int(max_chunk_length_sec * sample_rate)
+
+    def n_windows(length):
+        return max(0, -(-(length - clip_samples) // stride_samples))
+
+    if n_samples < max_chunk:
+        return [(0, n_windows(n_samples))]
+    out = []
+    for offset in range(0, n_samples, max_chunk):
+        if offset + max_chunk > n_samples:
+            out.append((offset, n_windows(min(max_chunk, n_samples - offset))))
+        else:
+            out.append((offset, n_windows(n_samples - offset)))
+    return out
+
+
 def calculate_streaming_accuracy(model, model_settings, flag_list, existing_inferences=None):
     assert len(set([f.wav for f in flag_list])) == 1, "can only process one wav"
     assert len(set([f.clip_duration_ms for f in flag_list])) == 1, "cannot vary"
@@ -116,6 +139,21 @@ def calculate_streaming_accuracy(model, model_settings, flag_list, existing_infe
         device_probs = stream_inferences(model, model_settings, audio, sample_rate, f0.clip_duration_ms,
                                          f0.clip_stride_ms, keep_on_device=True)
         inferences = device_probs.cpu().numpy()
+        # the matrix the reference RETURNS (and eval_stream_test saves) repeats the windows of the chunk tails for audio
+        # of >= max_chunk_length_sec (its inverted chunk branch, see reference_chunk_rows): same rows, same order
+        extra = []
+        for offset, n_w in reference_chunk_rows(audio.shape[0], sample_rate, clip_duration_samples, clip_stride_samples,
+                                                f0.max_chunk_length_sec)[1:]:
+            if n_w <= 0:
+                continue
+            if offset % clip_stride_samples == 0:        # those windows are windows of the whole signal: same rows
+                w0 = offset // clip_stride_samples
+                extra.append(inferences[w0:w0 + n_w])
+            else:
+                extra.append(stream_inferences(model, model_settings, audio[offset:offset + int(f0.max_chunk_length_sec * sample_rate)],
+                                               sample_rate, f0.clip_duration_ms, f0.clip_stride_ms))
+        if extra:
+            inferences = np.concatenate([inferences] + extra, axis=0)
     results = []
     for FLAGS in flag_list:
         res_thresh = {}

@@ -217,3 +217,28 @@ def test_bench_reference_arm_runs_on_cpu():
     assert d["impl"] == "reference" and d["unit"] == "utterances/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_reference_chunk_row_layout():
+    """Rows of the inferences matrix the reference returns for long audio (its inverted chunk branch,
+    batch_streaming_analysis.py:72-86): restated here line by line and compared with reference_chunk_rows."""
+    from multilingual_kws_b200.embedding.batch_streaming_analysis import reference_chunk_rows
+
+    def reference(n, sr, clip, stride, max_sec):
+        audio = np.arange(n)
+        max_chunk = max_sec * sr
+        chunks = []
+        if n < max_chunk:
+            chunks.append(audio)
+        else:
+            for offset in range(0, n, max_chunk):
+                if offset + max_chunk > n:
+                    chunks.append(audio[offset:offset + max_chunk])
+                else:
+                    chunks.append(audio[offset:])
+        return [(int(c[0]), int(np.ceil((c.shape[0] - clip) / stride))) for c in chunks]
+
+    for n in (16000 * 5, 16000 * 1200 - 1, 16000 * 1200, 16000 * 1800, 16000 * 1800 + 123, 16000 * 3000):
+        assert reference_chunk_rows(n, 16000, 16000, 320, 1200) == reference(n, 16000, 16000, 320, 1200), n
+    # 30 minutes at the default 20 ms hop (BASELINE config 5): 89 950 windows + the 29 950 of the last 10 minutes again
+    assert reference_chunk_rows(16000 * 1800, 16000, 16000, 320, 1200) == [(0, 89950), (19200000, 29950)]

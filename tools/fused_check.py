@@ -100,7 +100,7 @@ def main():
     EO.forward(w, feats, calibrate_bn=True)
     model = EmbeddingModel(w)
     out = torch.empty((B, 1024), device="cuda")
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         model.set_fuse(mode)
         for _ in range(3):
             model.forward_device(xb, out=out)
