@@ -295,8 +295,9 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- e2e: public API, host buffers (pinned), H2D + D2H inside the timed region
     from multilingual_kws_b200.pipeline import EmbedPipeline
-    pipe = EmbedPipeline(fe, emb_model, n_samples=16000, sub_batch=B, depth=2 * args.pipe_streams, streams=args.pipe_streams,
-                         sm_budget=ov_budget)
+    sub_b = args.pipe_sub_batch or B
+    pipe = EmbedPipeline(fe, emb_model, n_samples=16000, sub_batch=sub_b, depth=2 * args.pipe_streams * max(1, B // sub_b),
+                         streams=args.pipe_streams, sm_budget=ov_budget)
     # host buffers: two input sets in write-combined pinned memory (kws_host_alloc), two pinned result buffers
     pcm_pinned2 = [pipe.alloc_input(B), pipe.alloc_input(B)]
     pcm_pinned2[0].copy_(torch.from_numpy(pcm_host))
@@ -759,6 +760,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-finetune-e2e", action="store_true", help="skip the transfer_learn() end-to-end timing")
     ap.add_argument("--pipe-streams", type=int, default=3, help="compute streams the host pipeline / overlapped figure rotate over")
+    ap.add_argument("--pipe-sub-batch", type=int, default=0, help="clips per pipeline job of the e2e path (0 = the whole step)")
     ap.add_argument("--sm-budget", default="", help="head,tail SM budget of the throughput schedule (default: the pipeline's)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying the CUDA graph")
     args = ap.parse_args()
