@@ -100,6 +100,10 @@ int kws_embed_set_chunk(kws_embed_t* m, int chunk);
 int kws_embed_set_chunk_late(kws_embed_t* m, int chunk);
 /* 1 (default): capture the launch list of a forward pass into a CUDA graph per (buffers, batch) and replay it */
 int kws_embed_set_graph(kws_embed_t* m, int enable);
+/* The frozen part of the network only: ops 0 .. tap_op, whose output (16-bit NHWC) is copied to d_tap; no embedding is
+   written.  The trainable tail of phase 2 (transfer_learning.py:97-112) starts from that tensor. */
+int kws_embed_forward_until(kws_embed_t* m, const float* d_feats, int batch, void* d_workspace, size_t ws_bytes, int tap_op,
+                            void* d_tap, void* stream);
 /* Schedule of the network's tail (blocks 4a..7a + top conv, maps of <= 7x5 pixels): 0 = layer by layer (expand GEMM,
    depthwise + pool, SE GEMMs, gating, project GEMM: six launches per block), 1 = one fused tcgen05 launch per MBConv
    block, 2 (default) = runs of consecutive blocks (and the top conv + average pool) per launch.  Same results up to
@@ -156,6 +160,11 @@ int kws_head_reset_optimizer(kws_head_t* h);
 /* d(sum of losses) / d(embedding) [B, in_dim] fp32 of the batch of the last kws_head_grad call: what flows into the
    embedding when its top layers train too (transfer_learning.py:97-112, backprop_into_embedding=True). */
 int kws_head_input_grad(kws_head_t* h, int B, float* d_demb, void* stream);
+/* kws_head_apply_adam with the step size read from device memory (kws_train_lr_step); graph-capturable; does NOT advance
+   kws_head_step_count (a capture executes nothing, a replay is not seen by the host) */
+int kws_head_apply_adam_dev(kws_head_t* h, const float* d_flat, const float* d_lr_t, void* stream);
+/* reports `steps` executed kws_head_apply_adam_dev updates (keeps kws_head_step_count in step) */
+int kws_head_advance_step_count(kws_head_t* h, long long steps);
 
 /* ---------------------------------------------------------------------------------------------
  * Fine-tune backward through the top of the embedding — replaces what Keras / TensorFlow autodiff executes in the
@@ -190,8 +199,11 @@ int kws_train_colsum(const void* d_x, int rows, int cols, float* d_out, void* st
    the global batch with respect to the BN-folded weight, g = grad * row_scale[row] / (*d_count * loss_scale);
    d_out16 / d_out32 (optional) receive the folded 16-bit / fp32 copy the forward kernels read. */
 int kws_train_adam(float* d_param, float* d_m, float* d_v, const float* d_grad, size_t n, int cols, const float* d_row_scale,
-                   const float* d_count, float loss_scale, float lr, long long step, float beta1, float beta2, float eps,
-                   void* d_out16, float* d_out32, void* stream);
+                   const float* d_count, float loss_scale, float lr, long long step, const float* d_lr_t, float beta1,
+                   float beta2, float eps, void* d_out16, float* d_out32, void* stream);
+/* *d_step += 1; *d_lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t): with d_lr_t passed to kws_train_adam /
+   kws_head_apply_adam_dev (lr, step ignored) a whole optimisation step can be captured in a CUDA graph and replayed */
+int kws_train_lr_step(long long* d_step, float lr, float beta1, float beta2, float* d_lr_t, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Streaming post-processor — replaces the per-window Python loop

@@ -45,6 +45,7 @@ SIGNATURES = {
     "kws_embed_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "kws_embed_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "kws_embed_forward_budget": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "kws_embed_forward_until": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
     "kws_embed_forward_tap": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
     "kws_gemm_h16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                              c_int, c_int, c_void_p]),
@@ -74,7 +75,10 @@ SIGNATURES = {
     "kws_train_act_bwd": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_void_p]),
     "kws_train_colsum": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "kws_train_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_float, c_float,
-                               ctypes.c_longlong, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+                               ctypes.c_longlong, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "kws_train_lr_step": (c_int, [c_void_p, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "kws_head_apply_adam_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kws_head_advance_step_count": (c_int, [c_void_p, ctypes.c_longlong]),
     "kws_stream_detect": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_double, ctypes.c_double, c_int, c_void_p,
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "kws_augment_pcm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,

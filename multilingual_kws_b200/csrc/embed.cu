@@ -149,6 +149,7 @@ struct kws_embed {
   double flops_per_clip = 0;
   // Fused tail (mbconv_fused.cu): 0 = layer by layer, 1 = one launch per MBConv block, 2 = runs of blocks per launch
   int fuse = 0;                        // (default stays layer-wise until the fused kernel wins in the graph; see kws_embed_set_fuse)
+  int stop_after_tap = 0;              // kws_embed_forward_until: run only the ops up to (and including) the tapped one
   std::vector<FusedBlock> fblocks;
   std::vector<FusedBlockInfo> finfos;  // fblocks[i].info, contiguous (the launcher takes an array)
   FusedBlockDev* d_fblocks = nullptr;  // device array, same order as fblocks (+ the top-conv pseudo-block at the end)
@@ -825,6 +826,7 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
       if (host_op_ms) { KWS_CUDA_CHECK(cudaEventRecord(evs[ev_i++], st)); ev_op.push_back(-1); }
       int trunk = 0;                    // buffer holding the current block input: 0 = X, 2 = D (after a fused launch)
       for (int oi = op_lo; oi < op_hi; ++oi) {
+        if (m->stop_after_tap && tap_op >= 0 && oi > tap_op) break;
         const Op& op = m->ops[oi];
         const int sms = oi >= m->tail_op ? sms_tail : sms_head;
         const FusedSegment* sg = nullptr;
@@ -913,6 +915,19 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
 extern "C" int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
                                      size_t ws_bytes, int tap_op, void* d_tap, void* stream) {
   return embed_forward_impl(m, d_feats, batch, d_emb, d_workspace, ws_bytes, tap_op, d_tap, nullptr, stream);
+}
+
+// The frozen part of the network only: runs ops 0 .. tap_op and copies that op's output (16-bit NHWC) to d_tap; nothing
+// after it is executed and no embedding is written.  Used by the phase-2 fine-tune step, whose trainable tail starts at the
+// tapped tensor (finetune.TailTrainer).
+extern "C" int kws_embed_forward_until(kws_embed_t* m, const float* d_feats, int batch, void* d_workspace, size_t ws_bytes,
+                                       int tap_op, void* d_tap, void* stream) {
+  KWS_REQUIRE(m && d_tap && tap_op >= 0 && tap_op + 1 < (int)m->ops.size(), "kws_embed_forward_until: bad argument");
+  m->stop_after_tap = 1;
+  float dummy;
+  const int rc = embed_forward_impl(m, d_feats, batch, &dummy, d_workspace, ws_bytes, tap_op, d_tap, nullptr, stream);
+  m->stop_after_tap = 0;
+  return rc;
 }
 
 extern "C" int kws_embed_forward(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,

@@ -230,10 +230,11 @@ head_grad_sums_kernel(const float* __restrict__ emb, int B, HeadDims D, const fl
 }
 
 __global__ void head_adam_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
-                                 const float* __restrict__ flat, int n_params, float lr_t, float beta1, float beta2,
-                                 float eps) {
+                                 const float* __restrict__ flat, int n_params, float lr_host,
+                                 const float* __restrict__ lr_dev, float beta1, float beta2, float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_params) return;
+  const float lr_t = lr_dev ? *lr_dev : lr_host;
   const float count = flat[n_params + 2];
   const float g = flat[i] / fmaxf(count, 1.0f);
   const float mi = beta1 * m[i] + (1.0f - beta1) * g;
@@ -384,9 +385,26 @@ extern "C" int kws_head_apply_adam(kws_head_t* h, const float* d_flat, float lr,
   h->t += 1;
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)h->beta2, (double)h->t)) / (1.0 - pow((double)h->beta1, (double)h->t));
   const int n = h->D.n_params;
-  head_adam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->params, h->m, h->v, d_flat, n, (float)lr_t,
+  head_adam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->params, h->m, h->v, d_flat, n, (float)lr_t, nullptr,
                                                                       h->beta1, h->beta2, h->eps);
   KWS_CUDA_CHECK(cudaGetLastError());
+  return KWS_OK;
+}
+
+// Same update with the bias-corrected step size read from device memory (kws_train_lr_step): the call can be captured
+// in a CUDA graph and replayed.  It does not count the step on the host (a capture executes nothing, a replay is not seen):
+// the caller reports executed steps with kws_head_advance_step_count.
+extern "C" int kws_head_apply_adam_dev(kws_head_t* h, const float* d_flat, const float* d_lr_t, void* stream) {
+  KWS_REQUIRE(h && d_flat && d_lr_t, "kws_head_apply_adam_dev: bad argument");
+  const int n = h->D.n_params;
+  head_adam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->params, h->m, h->v, d_flat, n, 0.0f, d_lr_t,
+                                                                      h->beta1, h->beta2, h->eps);
+  KWS_CUDA_CHECK(cudaGetLastError());
+  return KWS_OK;
+}
+extern "C" int kws_head_advance_step_count(kws_head_t* h, long long steps) {
+  KWS_REQUIRE(h && steps >= 0, "kws_head_advance_step_count: bad argument");
+  h->t += steps;
   return KWS_OK;
 }
 

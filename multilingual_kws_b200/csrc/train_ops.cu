@@ -219,9 +219,11 @@ __global__ void __launch_bounds__(kT) colsum_kernel(const uint16_t* __restrict__
 __global__ void __launch_bounds__(kT) adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                                   const float* __restrict__ grad, size_t n, int cols,
                                                   const float* __restrict__ row_scale, const float* __restrict__ count,
-                                                  float inv_loss_scale, float lr_t, float b1, float b2, float eps,
+                                                  float inv_loss_scale, float lr_host, const float* __restrict__ lr_dev,
+                                                  float b1, float b2, float eps,
                                                   uint16_t* __restrict__ out16, float* __restrict__ out32) {
   const float inv = inv_loss_scale / fmaxf(*count, 1.0f);
+  const float lr_t = lr_dev ? *lr_dev : lr_host;
   for (size_t i = (size_t)blockIdx.x * kT + threadIdx.x; i < n; i += (size_t)gridDim.x * kT) {
     const float rs = row_scale ? row_scale[i / cols] : 1.0f;
     const float g = grad[i] * rs * inv;
@@ -232,6 +234,15 @@ __global__ void __launch_bounds__(kT) adam_kernel(float* __restrict__ p, float* 
     p[i] = w;
     if (out16) out16[i] = __half_as_ushort(__float2half_rn(w * rs));
     if (out32) out32[i] = w * rs;
+  }
+}
+
+// step counter and bias-corrected step size on the device, so that a captured CUDA graph of a whole optimisation step can
+// be replayed without the host: t <- t + 1, lr_t = lr sqrt(1 - b2^t) / (1 - b1^t)
+__global__ void lr_step_kernel(long long* __restrict__ t, float lr, float b1, float b2, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long s = ++(*t);
+    out[0] = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)s)) / (1.0 - pow((double)b1, (double)s)));
   }
 }
 
@@ -327,14 +338,20 @@ extern "C" int kws_train_colsum(const void* d_x, int rows, int cols, float* d_ou
   colsum_kernel<<<(cols + kT - 1) / kT, kT, 0, ST(stream)>>>(static_cast<const uint16_t*>(d_x), rows, cols, d_out);
   LAUNCH_OK();
 }
+extern "C" int kws_train_lr_step(long long* d_step, float lr, float beta1, float beta2, float* d_lr_t, void* stream) {
+  KWS_REQUIRE(d_step && d_lr_t, "kws_train_lr_step: bad argument");
+  lr_step_kernel<<<1, 32, 0, ST(stream)>>>(d_step, lr, beta1, beta2, d_lr_t);
+  LAUNCH_OK();
+}
 extern "C" int kws_train_adam(float* d_param, float* d_m, float* d_v, const float* d_grad, size_t n, int cols,
                               const float* d_row_scale, const float* d_count, float loss_scale, float lr, long long step,
-                              float beta1, float beta2, float eps, void* d_out16, float* d_out32, void* stream) {
-  KWS_REQUIRE(d_param && d_m && d_v && d_grad && d_count && cols > 0 && step >= 1 && loss_scale > 0.0f,
+                              const float* d_lr_t, float beta1, float beta2, float eps, void* d_out16, float* d_out32,
+                              void* stream) {
+  KWS_REQUIRE(d_param && d_m && d_v && d_grad && d_count && cols > 0 && (d_lr_t || step >= 1) && loss_scale > 0.0f,
               "kws_train_adam: bad argument");
   if (n == 0) return KWS_OK;
-  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+  const double lr_t = d_lr_t ? 0.0 : (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
   adam_kernel<<<grid_for(n), kT, 0, ST(stream)>>>(d_param, d_m, d_v, d_grad, n, cols, d_row_scale, d_count, 1.0f / loss_scale,
-                                                  (float)lr_t, beta1, beta2, eps, static_cast<uint16_t*>(d_out16), d_out32);
+                                                  (float)lr_t, d_lr_t, beta1, beta2, eps, static_cast<uint16_t*>(d_out16), d_out32);
   LAUNCH_OK();
 }

@@ -141,8 +141,11 @@ class TailTrainer:
         self.head_flat = self.flat[self.n_tail:]
         self.count = self.head_flat[head.n_params + 2:head.n_params + 3]
         self.t = 0
+        self.d_step = torch.zeros(1, dtype=torch.int64, device=dev)       # Adam iteration count and step size on the device:
+        self.d_lr_t = torch.zeros(1, dtype=torch.float32, device=dev)     # a captured step replays without the host
         self._scratch = None
         self.saved = None
+        self._graph = None
 
     # ------------------------------------------------------------------ helpers
     def _tr(self, x: torch.Tensor) -> torch.Tensor:
@@ -173,8 +176,7 @@ class TailTrainer:
     # ------------------------------------------------------------------ forward
     def tail_input(self, feats: torch.Tensor) -> torch.Tensor:
         """Frozen part of the network: features -> block6d output [B * P, cin] fp16."""
-        _, tap = self.embedding.forward_device(feats, tap_op=self.tap_op)
-        return tap.view(-1, self.cin)
+        return self.embedding.forward_until(feats, self.tap_op).view(-1, self.cin)
 
     def forward_tail(self, x7: torch.Tensor, keep: bool) -> torch.Tensor:
         L = _lib.lib()
@@ -265,27 +267,67 @@ class TailTrainer:
         self._wgrad(dz_e, sv["x7"], self.p_exp)
 
     # ------------------------------------------------------------------ optimiser
-    def apply_adam(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7) -> None:
+    def apply_adam(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7, count: bool = True) -> None:
+        """One Keras-Adam update of tail + head (one optimiser, one iteration count — the head's betas / eps are its own and
+        equal these defaults).  The iteration count and the bias-corrected step size live on the device; count=False leaves
+        the host-side mirrors alone (used while the launches are being captured into a graph)."""
         L = _lib.lib()
-        self.t += 1
+        if count:
+            self.t += 1
+            _lib.check(L.kws_head_advance_step_count(self.head._h, 1))
+        _lib.check(L.kws_train_lr_step(self.d_step.data_ptr(), float(lr), beta1, beta2, self.d_lr_t.data_ptr(), _st()))
         for p in self.params:
             _lib.check(L.kws_train_adam(p.master.data_ptr(), p.m.data_ptr(), p.v.data_ptr(), p.grad.data_ptr(), p.master.numel(),
-                                        p.cols, _ptr(p.scale), self.count.data_ptr(), self.loss_scale, float(lr), self.t,
-                                        beta1, beta2, eps, p.w16.data_ptr(), _ptr(p.w32), _st()), "kws_train_adam")
+                                        p.cols, _ptr(p.scale), self.count.data_ptr(), self.loss_scale, float(lr), 0,
+                                        self.d_lr_t.data_ptr(), beta1, beta2, eps, p.w16.data_ptr(), _ptr(p.w32), _st()),
+                       "kws_train_adam")
             p.refresh_transpose()
-        self.head.apply_adam(self.head_flat, lr)
+        _lib.check(L.kws_head_apply_adam_dev(self.head._h, self.head_flat.data_ptr(), self.d_lr_t.data_ptr(), _st()))
 
-    def step(self, feats: torch.Tensor, labels: torch.Tensor, lr: float) -> Tuple[float, float]:
-        """One optimisation step on the LOCAL shard `feats`/`labels`; the gradients (sums) are all-reduced across the ranks
-        of torch.distributed.  Returns (mean loss, accuracy) of the global batch."""
+    def _step_body(self, feats: torch.Tensor, labels: torch.Tensor, lr: float, count: bool = True) -> None:
         import torch.distributed as dist
         self.forward_tail(self.tail_input(feats), keep=True)
         self.backward(labels)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)     # ~10.1 M floats (40 MB): tail + head + loss/acc scalars
-        n_p = self.head.n_params
-        stats = self.head_flat[n_p:n_p + 3].tolist()
-        self.apply_adam(lr)
+        self._stats.copy_(self.head_flat[self.head.n_params:self.head.n_params + 3])
+        self.apply_adam(lr, count=count)
+
+    _stats = None
+
+    def step(self, feats: torch.Tensor, labels: torch.Tensor, lr: float, graph: bool = True) -> Tuple[float, float]:
+        """One optimisation step on the LOCAL shard `feats`/`labels`; the gradients (sums) are all-reduced across the ranks
+        of torch.distributed.  Returns (mean loss, accuracy) of the global batch.
+
+        graph=True: the whole step (frozen embedding, tail forward, backward, all-reduce, Adam: ~150 launches issued from
+        Python, ~1 ms of host work against ~0.5 ms of device work) is captured into one CUDA graph per (batch size, lr) on
+        first use and replayed afterwards."""
+        if self._stats is None:
+            self._stats = torch.zeros(3, dtype=torch.float32, device=self.dev)
+        feats = feats.to(self.dev, torch.float32)
+        labels = labels.to(self.dev, torch.int32)
+        if not graph:
+            self._step_body(feats.contiguous(), labels.contiguous(), lr)
+        else:
+            key = (int(feats.shape[0]), float(lr))
+            g = self._graph if self._graph is not None and self._graph[0] == key else None
+            if g is None:
+                # eager step first (allocations, scratch buffers, NCCL warm-up happen outside the capture), then capture
+                self._step_body(feats.contiguous(), labels.contiguous(), lr)
+                sf, sl = feats.clone().contiguous(), labels.clone().contiguous()
+                cg = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(cg):
+                    self._step_body(sf, sl, lr, count=False)          # a capture executes nothing
+                self._graph = (key, cg, sf, sl)
+            else:
+                _, cg, sf, sl = g
+                sf.copy_(feats)
+                sl.copy_(labels)
+                cg.replay()
+                self.t += 1
+                _lib.check(_lib.lib().kws_head_advance_step_count(self.head._h, 1))
+        stats = self._stats.tolist()
         cnt = max(stats[2], 1.0)
         return stats[0] / cnt, stats[1] / cnt
 

@@ -206,6 +206,21 @@ class EmbeddingModel:
                        "kws_embed_forward")
         return (out, tap) if tap_op >= 0 else out
 
+    def forward_until(self, feats: torch.Tensor, tap_op: int) -> torch.Tensor:
+        """Runs only the ops up to `tap_op` and returns that op's output (16-bit [B, elems]): the frozen part of the
+        network in front of a trainable tail (finetune.TailTrainer)."""
+        if feats.dim() == 4 and feats.shape[-1] == 1:
+            feats = feats[..., 0]
+        feats = feats.to(device=self.device, dtype=torch.float32).contiguous()
+        B = feats.shape[0]
+        _, elems = self.op_names()[tap_op]
+        tap = torch.empty((B, elems), dtype=torch.float16 if self.dtype == "fp16" else torch.bfloat16, device=self.device)
+        if B:
+            ws = self._workspace(B)
+            _lib.check(_lib.lib().kws_embed_forward_until(self._h, feats.data_ptr(), B, ws.data_ptr(), ws.numel(), int(tap_op),
+                                                          tap.data_ptr(), _lib.current_stream_ptr()), "kws_embed_forward_until")
+        return tap
+
     def predict(self, specs, batch_size: int = 4096, verbose: int = 0) -> np.ndarray:
         """Keras-style predict: host array [N,49,40] / [N,49,40,1] -> np.float32 [N, output_dim]."""
         x = torch.as_tensor(np.asarray(specs, dtype=np.float32))

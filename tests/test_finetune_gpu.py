@@ -97,6 +97,13 @@ def test_adam_steps_track_keras_adam(setup):
     print("oracle", np.round(losses_o, 4))
     assert losses_o[-1] < losses_o[0] * 0.9                      # the steps do train
     assert np.abs(np.array(losses_g) - np.array(losses_o)).max() < 0.02
+    assert trainer.t == 12 and trainer.head.step_count == 12 and int(trainer.d_step.item()) == 12   # 1 eager + 11 replays
+    # graph replay == eager launches: a second trainer stepping without the graph lands on the same parameters
+    eager = TailTrainer(EmbeddingModel(w), Head.from_params(hp))
+    for _ in range(12):
+        eager.step(x, y, 1e-4, graph=False)
+    for pg, pe in zip(trainer.params, eager.params):
+        assert torch.equal(pg.master, pe.master), pg.name
     new = trainer.export_weights()
     for k in ("dense_2/kernel", "top_conv/kernel", "block7a_expand_conv/kernel", "block7a_dwconv/depthwise_kernel"):
         moved = rel_err(p[k].detach().numpy(), w[k])             # how far training moved the tensor
