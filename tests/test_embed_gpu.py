@@ -152,10 +152,16 @@ def test_trained_weight_regime(kws_lib, feats):
     want = EO.forward(w, feats).numpy()
     got = EmbeddingModel(w).predict(feats)
     cos = EO.cosine(got, want)
-    print(f"trained regime: min cosine {cos.min():.6f} rel err {rel_err(got, want):.5f} "
-          f"(cosine between two clips {EO.cosine(want[0], want[1]):.3f})")
-    assert EO.cosine(want[0], want[1]) < 0.99                   # not collapsed
-    assert cos.min() >= 0.999
+    # a trained embedding carries a large component common to all clips (cosine between clips of different classes
+    # 0.95 ... 0.995 from run to run: cuDNN training is not deterministic), so parity is also checked on what
+    # distinguishes the clips: the embeddings minus their mean
+    mean = want.mean(axis=0)
+    spread = np.linalg.norm(want - mean) / np.linalg.norm(want)
+    cen = EO.cosine(got - mean, want - mean)
+    print(f"trained regime: min cosine {cos.min():.6f} rel err {rel_err(got, want):.5f}; spread of the embeddings around "
+          f"their mean {spread:.3f}, min cosine of the centred embeddings {cen.min():.5f}")
+    assert spread > 0.02                                        # not collapsed to a constant
+    assert cos.min() >= 0.999 and cen.min() >= 0.995
 
 
 def test_monolingual_head_sizes(kws_lib, feats):
