@@ -744,8 +744,23 @@ def run_ours(args, rank, local_rank, world):
         }
         print(json.dumps(out))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Leaving: every measurement is printed.  Tearing the NCCL communicator down (barrier + destroy_process_group) was
+        # seen to HANG at N = 8 once TailTrainer.step had captured its all-reduce into a CUDA graph (fine at N = 2), so the
+        # ranks leave without touching NCCL again: the others wait on the rendezvous store (plain TCP) until rank 0 has
+        # printed its line, then every process exits.
+        import datetime
+        sys.stdout.flush()
+        sys.stderr.flush()
+        try:
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                store.set("kws_bench_done", "1")
+                time.sleep(1.0)                      # let the others read the key while the store (hosted here) is alive
+            else:
+                store.wait(["kws_bench_done"], datetime.timedelta(seconds=300))
+        except Exception:
+            pass
+        os._exit(0)
 
 
 def main():
