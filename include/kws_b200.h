@@ -104,10 +104,11 @@ int kws_embed_set_graph(kws_embed_t* m, int enable);
    written.  The trainable tail of phase 2 (transfer_learning.py:97-112) starts from that tensor. */
 int kws_embed_forward_until(kws_embed_t* m, const float* d_feats, int batch, void* d_workspace, size_t ws_bytes, int tap_op,
                             void* d_tap, void* stream);
-/* Schedule of the network's tail (blocks 4a..7a + top conv, maps of <= 7x5 pixels): 0 = layer by layer (expand GEMM,
-   depthwise + pool, SE GEMMs, gating, project GEMM: six launches per block), 1 = one fused tcgen05 launch per MBConv
-   block, 2 (default) = runs of consecutive blocks (and the top conv + average pool) per launch.  Same results up to
-   16-bit rounding of the intermediates the fused kernel keeps in fp32. */
+/* Schedule of the network's tail (blocks 4a..7a + top conv, maps of <= 7x5 pixels): 0 (default) = layer by layer (expand
+   GEMM, depthwise + pool, SE GEMMs, gating, project GEMM: six launches per block), 1 = one fused tcgen05 launch per
+   MBConv block, 2 = runs of consecutive blocks (and the top conv + average pool) per launch, 3 = runs of the blocks
+   with <= 672 expanded channels only.  Same results up to 16-bit rounding of the intermediates the fused kernel keeps
+   in fp32.  The fused schedules cut launches (81 -> 18) and DRAM traffic, not time. */
 int kws_embed_set_fuse(kws_embed_t* m, int mode);
 /* kernel launches one forward pass of `batch` clips issues */
 int kws_embed_launches(const kws_embed_t* m, int batch);
@@ -120,7 +121,7 @@ int kws_embed_forward(kws_embed_t* m, const float* d_feats, int batch, float* d_
  * (0 = all SMs), so the tail's persistent CTAs leave room for a neighbouring pass.  Same results as kws_embed_forward. */
 int kws_embed_forward_budget(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
                              size_t ws_bytes, int sm_head, int sm_tail, void* stream);
-/* same, additionally copying the output of op `tap_op` (bf16 NHWC; fp32 for the last op) to d_tap */
+/* same, additionally copying the output of op `tap_op` (16-bit NHWC; fp32 for the last op) to d_tap */
 int kws_embed_forward_tap(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace,
                           size_t ws_bytes, int tap_op, void* d_tap, void* stream);
 

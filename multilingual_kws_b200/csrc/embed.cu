@@ -5,12 +5,12 @@
 // distance_filtering.py:12-27; architecture train_multilingual_embedding.py:66-83).
 //
 // At create time the Keras-named fp32 weights are folded for inference (BatchNorm -> scale/shift of the
-// preceding conv, eps 1e-3), converted to the layouts the kernels want (K-major bf16 for every tensor-core
-// contraction, fp32 for depthwise / SE / biases) and uploaded once.  A forward pass is a fixed list of
+// preceding conv, eps 1e-3), converted to the layouts the kernels want (K-major 16-bit — fp16 by default, bf16 on request —
+// for every tensor-core contraction, fp32 for depthwise / SE / biases) and uploaded once.  A forward pass is a fixed list of
 // launches on the caller's stream: stem conv, then per MBConv block
 //   [expand 1x1 GEMM + BN + swish] -> [depthwise + BN + swish + SE, fused] -> [project 1x1 GEMM + BN (+ residual)]
 // then top 1x1 GEMM + BN + swish + 2x2 average pool (fused epilogue) and the three dense GEMMs.
-// Activations are NHWC bf16 in three ping-pong workspace buffers; the batch is walked in chunks so
+// Activations are NHWC 16-bit in three ping-pong workspace buffers; the batch is walked in chunks so
 // one chunk's inter-layer activations stay resident in the 126 MB L2.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -193,7 +193,7 @@ struct Builder {
     }
     return true;
   }
-  // 1x1 conv / dense kernel [K][N] (Keras) -> bf16 [N][K] with per-output scale
+  // 1x1 conv / dense kernel [K][N] (Keras) -> 16-bit [N][K] with per-output scale
   const uint16_t* gemm_weight(const std::string& name, int K, int N, const std::vector<float>* scale) {
     const HostTensor* t = get(name, (size_t)K * N);
     if (!t) return nullptr;
@@ -724,7 +724,7 @@ extern "C" size_t kws_embed_workspace_bytes(const kws_embed_t* m, int batch) {
   return (early + late + se_scratch) * 2 + 4096;
 }
 
-// tap_op >= 0: additionally copy the output of op `tap_op` (bf16 NHWC, or fp32 for the last op) to d_tap.
+// tap_op >= 0: additionally copy the output of op `tap_op` (16-bit NHWC, or fp32 for the last op) to d_tap.
 static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb, void* d_workspace, int tap_op,
                    void* d_tap, float* host_op_ms, cudaStream_t st, int sm_head, int sm_tail);
 

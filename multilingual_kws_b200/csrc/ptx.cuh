@@ -9,16 +9,6 @@ namespace kws {
 namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -72,17 +62,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* desc, uint64_t* b
       : "memory");
 }
 
-// TMA store: swizzled smem tile -> global, clipped at the tensor bounds
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* desc, const void* src_smem, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(desc)),
-               "r"(smem_u32(src_smem)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // ---- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
@@ -119,16 +98,9 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// start>>4 [0,14), LBO>>4 [16,30) (ignored for swizzled K-major, canonical 1), SBO>>4 [32,46) = 1024 B between
-// 8-row groups, version [46,48) = 1 on sm_100, layout [61,64) = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
-  const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
-  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-  return ((uint64_t)hi << 32) | lo;
-}
-// Same for a tile whose rows are row_bytes = 32 / 64 / 128 B wide (SWIZZLE_32B / 64B / 128B; layout codes 6 / 4 / 2):
-// SBO = 8 rows * row_bytes.
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30) (ignored
+// for swizzled K-major, canonical 1), SBO>>4 [32,46) = bytes between 8-row groups, version [46,48) = 1 on sm_100,
+// layout [61,64) = 2 / 4 / 6 (SWIZZLE_128B / 64B / 32B) for tiles whose rows are 128 / 64 / 32 B wide: SBO = 8 rows * row_bytes.
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t row_bytes) {
   const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
   const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);

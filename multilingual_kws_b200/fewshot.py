@@ -73,6 +73,13 @@ class Head:
     def grad(self, emb: torch.Tensor, labels: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Flat [dW1|db1|dW2|db2|loss_sum|n_correct|n] for the local batch (sums -> all-reduce(sum)-able)."""
         emb = emb.to(self.device, torch.float32).contiguous()
+        if not (isinstance(labels, torch.Tensor) and labels.is_cuda):
+            # Keras' sparse categorical cross-entropy rejects labels outside [0, classes); device-resident labels are
+            # not read back here (that would synchronise every step): the caller vouches for them
+            lab = torch.as_tensor(np.asarray(labels))
+            if lab.numel() and (int(lab.min()) < 0 or int(lab.max()) >= self.classes):
+                raise ValueError(f"labels must lie in [0, {self.classes}): got [{int(lab.min())}, {int(lab.max())}]")
+            labels = lab
         labels = labels.to(self.device, torch.int32).contiguous()
         flat = out if out is not None else self._flat
         _lib.check(_lib.lib().kws_head_grad(self._h, emb.data_ptr(), labels.data_ptr(), emb.shape[0], flat.data_ptr(),
