@@ -57,6 +57,16 @@ class EmbedPipeline:
         self._downloaded = [torch.cuda.Event() for _ in range(depth)]
         self._jobs = 0                      # jobs enqueued since construction (slot = job % depth)
         self.sm_budget = sm_budget if sm_budget is not None else (self.SM_BUDGET if int(streams) > 1 else None)
+        # The library captures a forward pass into a CUDA graph the second time it meets the same buffers (one-off
+        # buffers are not worth a capture).  The slots are fixed, so meet each of them twice now: the first full job on
+        # every slot is then already a graph replay instead of a capture inside the caller's latency.
+        for s in range(depth):
+            with torch.cuda.stream(self._compute[s % len(self._compute)]):
+                self._feat[s].zero_()
+                for _ in range(2):
+                    self.model.forward_device(self._feat[s], out=self._emb[s], workspace=self._ws[s], sm_budget=self.sm_budget)
+        for c in self._compute:
+            c.synchronize()
 
     def alloc_input(self, batch: int) -> torch.Tensor:
         """int16 [batch, n_samples] upload buffer in write-combined pinned memory (fill it with PCM, do not read it
