@@ -579,170 +579,6 @@ se_scale_kernel(uint16_t* __restrict__ y, const uint16_t* __restrict__ gates, in
   }
 }
 
-
-// ---- squeeze-excite of the wide layers in ONE launch on the CUDA cores: FC1 (+ swish), FC2 (+ sigmoid) and the gating pass.
-// The fully-connected pair is 0.2 MFLOP per clip — nothing for a tensor core to win — and as two GEMM launches plus a
-// gating launch it cost three dependent-kernel boundaries per block (~20 us of ~45 per MBConv block at 1024 clips).  Here a
-// CTA takes kG clips: the pooled means go to shared memory as fp32, a warp per squeeze unit walks W1's row with 16-byte
-// loads (coalesced over the channels, every weight reused for the kG clips), a thread per channel walks W2's row, the
-// gates stay in shared memory (fp32) and scale the CTA's own clips in place.  Weights come from L2 (<= 221 KB per
-// layer); nothing but the activation is written.
-// Shared layout of a [C] vector: two planes of C/2 floats — plane 0 holds elements 0..3 of every group of eight
-// channels, plane 1 elements 4..7 — so a lane that owns channel group c8 reads two float4 at stride 16 B (no bank conflict).
-constexpr int kSeRowVecs = 5;    // 16-byte vectors per lane of one W1 row: C <= 32 * 8 * 5 = 1280 channels
-constexpr int kSeSqVecs = 8;     // 16-byte vectors of one W2 row: se_pad <= 64 squeeze units
-__device__ __forceinline__ int se_plane_idx(int c, int C) { return ((c & 4) ? (C >> 1) : 0) + ((c >> 3) << 2) + (c & 3); }
-
-template <int kG>
-__global__ void __launch_bounds__(256)
-se_gate_kernel(uint16_t* __restrict__ y, const uint16_t* __restrict__ pooled, const uint16_t* __restrict__ w1,
-               const float* __restrict__ b1, const uint16_t* __restrict__ w2, const float* __restrict__ b2, int batch,
-               int npix, int C, int se, int se_pad, int bf16) {
-  extern __shared__ float se_sm[];
-  float* vec_s = se_sm;                  // [kG][C]  pooled means, then gates (planar layout above)
-  float* sq_s = se_sm + kG * C;          // [kG][se_pad] squeeze activations
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int C8 = C >> 3, half_c = C >> 1;
-  ptx::pdl_launch_dependents();
-  ptx::pdl_wait();
-  for (int grp = blockIdx.x; grp * kG < batch; grp += gridDim.x) {
-    const int clip0 = grp * kG;
-    const int ng = batch - clip0 < kG ? batch - clip0 : kG;
-    // 1. pooled means -> fp32 planes (zeros for the clips past the end of the batch)
-    for (int i = tid; i < kG * C8; i += 256) {
-      const int g = i / C8, c8 = i - g * C8;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (g < ng) v = *(reinterpret_cast<const uint4*>(pooled + (size_t)(clip0 + g) * C) + c8);
-      const float2 a = ptx::unpack_h2(v.x, bf16), b = ptx::unpack_h2(v.y, bf16);
-      const float2 c = ptx::unpack_h2(v.z, bf16), d = ptx::unpack_h2(v.w, bf16);
-      *reinterpret_cast<float4*>(vec_s + g * C + c8 * 4) = make_float4(a.x, a.y, b.x, b.y);
-      *reinterpret_cast<float4*>(vec_s + g * C + half_c + c8 * 4) = make_float4(c.x, c.y, d.x, d.y);
-    }
-    for (int i = tid; i < kG * se_pad; i += 256) sq_s[i] = 0.0f;      // padding units stay 0 (W2's padding columns are 0 too)
-    __syncthreads();
-    // 2. FC1: squeeze units j and j + 8 on warp j % 8; both weight rows (<= kSeRowVecs 16-byte vectors per lane each) are
-    //    requested before the first is used, so a warp waits for L2 once per pair of units
-    for (int j0 = warp; j0 < se; j0 += 16) {
-      const int j1 = j0 + 8;
-      const bool has1 = j1 < se;
-      const uint4* r0 = reinterpret_cast<const uint4*>(w1 + (size_t)j0 * C);
-      const uint4* r1 = reinterpret_cast<const uint4*>(w1 + (size_t)(has1 ? j1 : j0) * C);
-      uint4 wv0[kSeRowVecs], wv1[kSeRowVecs];
-#pragma unroll
-      for (int u = 0; u < kSeRowVecs; ++u) {
-        const int c8 = lane + 32 * u;
-        wv0[u] = c8 < C8 ? __ldg(r0 + c8) : make_uint4(0u, 0u, 0u, 0u);
-        wv1[u] = c8 < C8 ? __ldg(r1 + c8) : make_uint4(0u, 0u, 0u, 0u);
-      }
-      float acc0[kG], acc1[kG];
-#pragma unroll
-      for (int g = 0; g < kG; ++g) acc0[g] = acc1[g] = 0.0f;
-#pragma unroll
-      for (int u = 0; u < kSeRowVecs; ++u) {
-        const int c8 = lane + 32 * u;
-        if (c8 < C8) {
-          const float2 a0 = ptx::unpack_h2(wv0[u].x, bf16), a1 = ptx::unpack_h2(wv0[u].y, bf16);
-          const float2 a2 = ptx::unpack_h2(wv0[u].z, bf16), a3 = ptx::unpack_h2(wv0[u].w, bf16);
-          const float2 b0 = ptx::unpack_h2(wv1[u].x, bf16), b1v = ptx::unpack_h2(wv1[u].y, bf16);
-          const float2 b2v = ptx::unpack_h2(wv1[u].z, bf16), b3 = ptx::unpack_h2(wv1[u].w, bf16);
-#pragma unroll
-          for (int g = 0; g < kG; ++g) {
-            const float4 p0 = *reinterpret_cast<const float4*>(vec_s + g * C + c8 * 4);
-            const float4 p1 = *reinterpret_cast<const float4*>(vec_s + g * C + half_c + c8 * 4);
-            float t = acc0[g];
-            t = fmaf(a0.x, p0.x, t); t = fmaf(a0.y, p0.y, t); t = fmaf(a1.x, p0.z, t); t = fmaf(a1.y, p0.w, t);
-            t = fmaf(a2.x, p1.x, t); t = fmaf(a2.y, p1.y, t); t = fmaf(a3.x, p1.z, t); t = fmaf(a3.y, p1.w, t);
-            acc0[g] = t;
-            t = acc1[g];
-            t = fmaf(b0.x, p0.x, t); t = fmaf(b0.y, p0.y, t); t = fmaf(b1v.x, p0.z, t); t = fmaf(b1v.y, p0.w, t);
-            t = fmaf(b2v.x, p1.x, t); t = fmaf(b2v.y, p1.y, t); t = fmaf(b3.x, p1.z, t); t = fmaf(b3.y, p1.w, t);
-            acc1[g] = t;
-          }
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < kG; ++g) {
-        float t0 = acc0[g], t1 = acc1[g];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          t0 += __shfl_xor_sync(0xffffffffu, t0, o);
-          t1 += __shfl_xor_sync(0xffffffffu, t1, o);
-        }
-        if (lane == 0) {
-          sq_s[g * se_pad + j0] = swish(t0 + __ldg(b1 + j0));
-          if (has1) sq_s[g * se_pad + j1] = swish(t1 + __ldg(b1 + j1));
-        }
-      }
-    }
-    __syncthreads();
-    // 3. FC2: channel c on thread c % 256, W2's row (se_pad <= 8 * kSeSqVecs halves) in registers, the next channel's row
-    //    requested before this one is used; the gates overwrite the pooled means
-    {
-      const int n8 = se_pad >> 3;
-      uint4 cur[kSeSqVecs], nxt[kSeSqVecs];
-#pragma unroll
-      for (int u = 0; u < kSeSqVecs; ++u)
-        cur[u] = (tid < C && u < n8) ? __ldg(reinterpret_cast<const uint4*>(w2 + (size_t)tid * se_pad) + u) : make_uint4(0u, 0u, 0u, 0u);
-      for (int c = tid; c < C; c += 256) {
-        const int cn = c + 256;
-#pragma unroll
-        for (int u = 0; u < kSeSqVecs; ++u)
-          nxt[u] = (cn < C && u < n8) ? __ldg(reinterpret_cast<const uint4*>(w2 + (size_t)cn * se_pad) + u) : make_uint4(0u, 0u, 0u, 0u);
-        float acc[kG];
-        const float bias = __ldg(b2 + c);
-#pragma unroll
-        for (int g = 0; g < kG; ++g) acc[g] = bias;
-#pragma unroll
-        for (int u = 0; u < kSeSqVecs; ++u) {
-          if (u < n8) {
-            const float2 wa = ptx::unpack_h2(cur[u].x, bf16), wb = ptx::unpack_h2(cur[u].y, bf16);
-            const float2 wc = ptx::unpack_h2(cur[u].z, bf16), wd = ptx::unpack_h2(cur[u].w, bf16);
-#pragma unroll
-            for (int g = 0; g < kG; ++g) {
-              const float4 s0 = *reinterpret_cast<const float4*>(sq_s + g * se_pad + u * 8);        // broadcast reads
-              const float4 s1 = *reinterpret_cast<const float4*>(sq_s + g * se_pad + u * 8 + 4);
-              float t = acc[g];
-              t = fmaf(wa.x, s0.x, t); t = fmaf(wa.y, s0.y, t); t = fmaf(wb.x, s0.z, t); t = fmaf(wb.y, s0.w, t);
-              t = fmaf(wc.x, s1.x, t); t = fmaf(wc.y, s1.y, t); t = fmaf(wd.x, s1.z, t); t = fmaf(wd.y, s1.w, t);
-              acc[g] = t;
-            }
-          }
-        }
-        const int pi = se_plane_idx(c, C);
-#pragma unroll
-        for (int g = 0; g < kG; ++g) vec_s[g * C + pi] = sigmoidf(acc[g]);
-#pragma unroll
-        for (int u = 0; u < kSeSqVecs; ++u) cur[u] = nxt[u];
-      }
-    }
-    __syncthreads();
-    // 4. gating pass over the CTA's clips: y[clip, p, c] *= gate[clip, c], 16-byte vectors
-    const int vec_per_clip = npix * C8;
-    const int step = 256 % C8;
-    for (int g = 0; g < ng; ++g) {
-      uint4* dst = reinterpret_cast<uint4*>(y) + (size_t)(clip0 + g) * vec_per_clip;
-      const float* gate = vec_s + g * C;
-      int c8 = tid % C8;
-#pragma unroll 4
-      for (int i = tid; i < vec_per_clip; i += 256) {
-        const uint4 v = dst[i];
-        const float4 g0 = *reinterpret_cast<const float4*>(gate + c8 * 4);
-        const float4 g1 = *reinterpret_cast<const float4*>(gate + half_c + c8 * 4);
-        float2 a;
-        uint4 o;
-        a = ptx::unpack_h2(v.x, bf16); o.x = ptx::pack_h2(a.x * g0.x, a.y * g0.y, bf16);
-        a = ptx::unpack_h2(v.y, bf16); o.y = ptx::pack_h2(a.x * g0.z, a.y * g0.w, bf16);
-        a = ptx::unpack_h2(v.z, bf16); o.z = ptx::pack_h2(a.x * g1.x, a.y * g1.y, bf16);
-        a = ptx::unpack_h2(v.w, bf16); o.w = ptx::pack_h2(a.x * g1.z, a.y * g1.w, bf16);
-        dst[i] = o;
-        c8 += step;
-        if (c8 >= C8) c8 -= C8;
-      }
-    }
-    __syncthreads();                     // the next group overwrites the planes
-  }
-}
-
 }  // namespace
 
 int launch_se_scale(void* d_y, const void* d_gates, int batch, int npix, int C, int bf16, int sm_count, cudaStream_t st) {
@@ -750,28 +586,6 @@ int launch_se_scale(void* d_y, const void* d_gates, int batch, int npix, int C, 
   const int grid = batch < sm_count * 8 ? batch : sm_count * 8;
   KWS_CUDA_CHECK(launch_pdl(se_scale_kernel, dim3(grid), dim3(256), 0, st, static_cast<uint16_t*>(d_y),
                             static_cast<const uint16_t*>(d_gates), batch, npix, C, bf16));
-  return KWS_OK;
-}
-
-int se_gate_max_channels() { return 32 * 8 * kSeRowVecs; }
-int se_gate_max_squeeze() { return 8 * kSeSqVecs; }
-
-int launch_se_gate(void* d_y, const void* d_pooled, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2,
-                   int batch, int npix, int C, int se, int se_pad, int bf16, int sm_count, cudaStream_t st) {
-  if (batch == 0) return KWS_OK;
-  KWS_REQUIRE(C % 8 == 0 && C <= se_gate_max_channels() && se_pad % 8 == 0 && se_pad <= se_gate_max_squeeze() && se >= 1 &&
-                  se <= se_pad, "se_gate: channels %d / squeeze units %d (padded %d)", C, se, se_pad);
-  // clips per CTA: every weight fetched from L2 serves kG clips; keep at least one CTA per SM
-  const int G = batch >= 4 * sm_count ? 4 : (batch >= 2 * sm_count ? 2 : 1);
-  const size_t smem = (size_t)G * (C + se_pad) * sizeof(float);
-  KWS_REQUIRE(smem <= 48 * 1024, "se_gate: %d channels do not fit shared memory", C);
-  const int groups = (batch + G - 1) / G;
-  const int grid = groups < sm_count * 4 ? groups : sm_count * 4;
-  void (*kern)(uint16_t*, const uint16_t*, const uint16_t*, const float*, const uint16_t*, const float*, int, int, int, int, int,
-               int) = G == 4 ? se_gate_kernel<4> : (G == 2 ? se_gate_kernel<2> : se_gate_kernel<1>);
-  KWS_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(256), smem, st, static_cast<uint16_t*>(d_y),
-                            static_cast<const uint16_t*>(d_pooled), static_cast<const uint16_t*>(d_w1), d_b1,
-                            static_cast<const uint16_t*>(d_w2), d_b2, batch, npix, C, se, se_pad, bf16));
   return KWS_OK;
 }
 

@@ -38,11 +38,4 @@ int launch_dwse(const void* d_x, int batch, const DwseParams& P, void* d_y, int 
 // y[clip, p, c] *= gates[clip, c]   (16-bit, in place; the gating pass of the external-SE path)
 int launch_se_scale(void* d_y, const void* d_gates, int batch, int npix, int C, int bf16, int sm_count, cudaStream_t st);
 
-// The whole squeeze-excite of a wide layer in one launch: gates = sigmoid(W2 swish(W1 pooled + b1) + b2) on the CUDA cores
-// (fp32 accumulation, 16-bit weights w1 [se_pad][C], w2 [C][se_pad]) and y[clip, p, c] *= gates[clip, c] in place.
-int se_gate_max_channels();   // widest layer / squeeze the kernel's register tiles cover
-int se_gate_max_squeeze();
-int launch_se_gate(void* d_y, const void* d_pooled, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2,
-                   int batch, int npix, int C, int se, int se_pad, int bf16, int sm_count, cudaStream_t st);
-
 }  // namespace kws

@@ -149,7 +149,6 @@ struct kws_embed {
   int bf16 = 0;                        // 16-bit storage / tensor-core operand type: 0 fp16 (default), 1 bf16
   double flops_per_clip = 0;
   // Fused tail (mbconv_fused.cu): 0 = layer by layer, 1 = one launch per MBConv block, 2 = runs of blocks per launch
-  int se_kernel = 1;                   // wide layers' squeeze-excite: 1 = one CUDA-core launch (FC1, FC2, gating), 0 = two GEMMs + gating pass
   int fuse = 0;                        // (default stays layer-wise until the fused kernel wins in the graph; see kws_embed_set_fuse)
   int stop_after_tap = 0;              // kws_embed_forward_until: run only the ops up to (and including) the tapped one
   std::vector<FusedBlock> fblocks;
@@ -264,8 +263,8 @@ static int build_fused_plan(kws_embed* m) {
   }
   // modes 2 and 3: greedy runs.  A run keeps growing while the merged launch still fits at least kMinGroup clips per CTA.
   // Mode 3 fuses only the blocks with <= 672 expanded channels (4a .. 6a: 12 pixels per clip, where one fused launch beats
-  // the six layer-wise ones); the 1152-channel blocks on 2x2 maps (6b .. 7a) are issue-bound in the fused kernel (their
-  // MMAs have N = 28 rows and cost the same ~148 cycles as N = 256) and stay layer-wise.
+  // the six layer-wise ones); the 1152-channel blocks on 2x2 maps (6b .. 7a) give a fused CTA only 28 rows per step
+  // (measured slower than their six layer-wise launches) and stay layer-wise.
   const int kMinGroup = 7;
   m->finfos.resize(n);
   for (int i = 0; i < n; ++i) m->finfos[i] = m->fblocks[i].info;
@@ -307,7 +306,6 @@ extern "C" int kws_embed_create(kws_embed_t** out, const void* blob, size_t byte
   KWS_REQUIRE(m != nullptr, "out of host memory");
   m->bf16 = act_dtype;
   if (const char* env = getenv("KWS_SE_IN_KERNEL")) m->se_via_gemm = atoi(env) ? 0 : 1;   // tuning knob (A/B measurements)
-  if (const char* env = getenv("KWS_SE_KERNEL")) m->se_kernel = atoi(env) ? 1 : 0;        // 0: the round-1 path (two GEMMs + gating pass)
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -696,7 +694,7 @@ extern "C" int kws_embed_launches(const kws_embed_t* m, int batch) {
   const int n_ops = (int)m->ops.size();
   int launches = 0;
   for (int i = 0; i < n_ops; ++i) {
-    int per = (m->ops[i].kind == kOpDwse && m->ops[i].dw.se_external) ? (m->se_kernel ? 2 : 4) : 1;   // dw+pool, SE (+ gating)
+    int per = (m->ops[i].kind == kOpDwse && m->ops[i].dw.se_external) ? 4 : 1;   // dw+pool, 2 SE GEMMs, gating
     for (const FusedSegment& c : m->segs[m->fuse])
       if (i >= c.op_lo && i <= c.op_hi) per = i == c.op_hi ? 1 : 0;               // one launch for the whole run
     launches += per * (i < m->split_op ? (batch + ce - 1) / ce : (batch + cl - 1) / cl);
@@ -887,10 +885,7 @@ static int run_ops(kws_embed_t* m, const float* d_feats, int batch, float* d_emb
           DwseParams P = op.dw;
           P.pooled_out = se_pooled;
           rc = launch_dwse(bufs[op.in_buf], nb, P, out_ptr, dwse_pick_group(P, m->max_smem, nb, sms), sms, st);
-          if (rc == KWS_OK && P.se_external && m->se_kernel && P.C <= se_gate_max_channels() && op.se_pad <= se_gate_max_squeeze()) {
-            rc = launch_se_gate(out_ptr, se_pooled, op.se_w1, op.se_b1, op.se_w2, P.b_se2, nb, P.Ho * P.Wo, P.C, P.se, op.se_pad,
-                                m->bf16, sms, st);
-          } else if (rc == KWS_OK && P.se_external) {
+          if (rc == KWS_OK && P.se_external) {
             GemmEpilogue e1;
             e1.bias = op.se_b1; e1.residual = nullptr; e1.out = se_squeeze; e1.ldo = op.se_pad; e1.ldr = op.se_pad;
             e1.act = kActSwish; e1.out_f32 = 0; e1.gap4 = 0; e1.bf16 = m->bf16;

@@ -788,8 +788,8 @@ int launch_mbconv_fused(const void* d_x, int batch, const FusedBlockDev* d_block
   KWS_REQUIRE(gmax >= 1, "mbconv_fused: block does not fit shared memory / TMEM");
   // KWS_FUSED_CLUSTER = 2 / 4: clusters of CTAs share every weight tile (one L2 read per cluster, multicast into all
   // rings).  Measured on the B200: identical phase times for 1, 2 and 4 — the weight stream is not what bounds the
-  // kernel (the issuer is: a tcgen05.mma with both operands in shared memory costs ~148 cycles whatever N is, see
-  // tools/microbench/mma_chain.cu), so the default stays 1 (all 148 SMs; clusters of 4 fit only 132).
+  // kernel (its ~40 dependent, latency-bound steps per block are), so the default stays 1 (all 148 SMs;
+  // clusters of 4 fit only 132).
   static const int cluster_env = [] { const char* e = getenv("KWS_FUSED_CLUSTER"); return e ? atoi(e) : 0; }();
   int C = (cluster_env == 2 || cluster_env == 4) ? cluster_env : 1;
   const int slots = C == 4 ? (sm_count * 132) / 148 : sm_count;

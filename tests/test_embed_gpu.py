@@ -137,28 +137,6 @@ def test_fused_tail_schedules_agree(setup, feats):
         model.set_fuse(0)
 
 
-def test_se_kernel_matches_gemm_path(kws_lib, setup, feats, monkeypatch):
-    """Wide layers' squeeze-excite: the one-launch CUDA-core kernel (default) against the round-1 path (two tcgen05 GEMMs
-    + gating pass, KWS_SE_KERNEL=0), for every clips-per-CTA variant (1 / 2 / 4, chosen from the batch) and ragged ends."""
-    from multilingual_kws_b200.model import EmbeddingModel
-    model, w, _, _ = setup
-    monkeypatch.setenv("KWS_SE_KERNEL", "0")
-    old = EmbeddingModel(w)
-    monkeypatch.delenv("KWS_SE_KERNEL")
-    assert old.launches(1024) == model.launches(1024) + 20         # 10 wide blocks (4b .. 7a): 4 launches -> 2
-    names = [n for n, _ in model.op_names()]
-    taps = [names.index(n) for n in ("block4b_se_excite", "block6d_se_excite", "block7a_se_excite")]
-    for batch in (40, 297, 597, 640):
-        x = torch.from_numpy(np.tile(feats, (-(-batch // feats.shape[0]), 1, 1))[:batch]).cuda()
-        x = x * torch.linspace(0.5, 1.5, batch, device="cuda")[:, None, None]      # no two clips alike
-        got, want = model.forward_device(x), old.forward_device(x)
-        assert torch.isfinite(got).all()
-        assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 5e-3, batch
-        for t in taps:
-            a, b = model.forward_device(x, tap_op=t)[1], old.forward_device(x, tap_op=t)[1]
-            assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) < 5e-3, (batch, names[t])
-
-
 def test_trained_weight_regime(kws_lib, feats):
     """Third weight regime: the torch restatement TRAINED for 150 Adam steps (BatchNorm in training mode) on a synthetic
     4-way task from plain Keras initialisation (no damping, no calibration) — oracle/effnet_train_oracle.py.  The
