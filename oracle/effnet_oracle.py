@@ -11,9 +11,12 @@ dependency absent from /root/reference; this restates its published architecture
 Rescaling(1/255) -> Normalization(un-adapted = identity) -> ZeroPadding2D(correct_pad)+Conv3x3 s2 VALID
 -> BN(eps 1e-3) -> swish -> 16 MBConv (expand 1x1/BN/swish, depthwise kxk [stride 2: correct_pad+VALID,
 else SAME]/BN/swish, SE with biases, project 1x1/BN, residual) -> Conv1x1 1280/BN/swish.
-PARITY UNPINNED: the pretrained checkpoint is a release asset that is not available offline and TF
-cannot run here; the oracle is pinned by Keras' parameter counts / output shapes
-and is deliberately independent of the product's layer table (it re-derives shapes on the fly).
+PARITY UNPINNED AGAINST KERAS: the pretrained checkpoint is a release asset that is not available offline
+and TF cannot run here.  Pins that do exist: Keras' parameter counts / output shapes, and
+tests/test_oracle_effnet_torchvision.py — torchvision's own EfficientNet-B0 implementation, loaded with this
+oracle's weights and given Keras' BN eps / stride-2 padding convention, reproduces every stage output and the
+embedding to 1e-9 (float64).  The oracle is deliberately independent of the product's layer table (it
+re-derives shapes on the fly).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
 """
