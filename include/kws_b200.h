@@ -98,7 +98,8 @@ int kws_embed_op_info(const kws_embed_t* m, int op, int* kind, double* flops_per
 int kws_embed_set_chunk(kws_embed_t* m, int chunk);
 /* clips per pass for the late (small-activation) layers; large values fill the SMs */
 int kws_embed_set_chunk_late(kws_embed_t* m, int chunk);
-/* 1 (default): capture the launch list of a forward pass into a CUDA graph per (buffers, batch) and replay it */
+/* 1 (default): capture the launch list of a forward pass into a CUDA graph per (buffers, batch, schedule) the second
+   time that key is met, and replay it from then on (one-off buffers run plain launches); 0: plain launches always */
 int kws_embed_set_graph(kws_embed_t* m, int enable);
 /* The frozen part of the network only: ops 0 .. tap_op, whose output (16-bit NHWC) is copied to d_tap; no embedding is
    written.  The trainable tail of phase 2 (transfer_learning.py:97-112) starts from that tensor. */
