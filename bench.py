@@ -442,9 +442,22 @@ def run_ours(args, rank, local_rank, world):
             m_solo.head.apply_adam(m_solo.head.grad(e_all, p_labels), 1e-3)
         a, b = m_dist.head.get_params(), m_solo.head.get_params()
         head_diff = float(np.abs(a - b).max())
+        # Adam divides the gradient by its own magnitude, so equal parameters do not prove an equal gradient SCALE:
+        # compare the all-reduced gradient sums themselves (shards + NCCL sum vs the whole batch on this rank)
+        lo_, hi_ = nb_ * rank // world, nb_ * (rank + 1) // world
+        g_solo = m_solo.head.grad(e_all, p_labels).clone()
+        g_dist = m_solo.head.grad(e_all[lo_:hi_].contiguous(), p_labels[lo_:hi_].contiguous()).clone()
+        dist.all_reduce(g_dist, op=dist.ReduceOp.SUM)
+        head_grad_rel = float((g_dist - g_solo).norm() / g_solo.norm())
         # (2) phase-2 steps: sharded + 40 MB all-reduce vs the whole batch on this rank alone
         t_dist = TailTrainer(emb_model, Head.keras_init(emb_model.output_dim, 18, 3, seed=6))
         t_solo = TailTrainer(emb_model, Head.keras_init(emb_model.output_dim, 18, 3, seed=6))
+        t_dist.forward_tail(t_dist.tail_input(p_specs[lo_:hi_].contiguous()), keep=True)
+        t_dist.backward(p_labels[lo_:hi_].contiguous())
+        dist.all_reduce(t_dist.flat, op=dist.ReduceOp.SUM)
+        t_solo.forward_tail(t_solo.tail_input(p_specs), keep=True)
+        t_solo.backward(p_labels)
+        tail_grad_rel = float((t_dist.flat - t_solo.flat).norm() / t_solo.flat.norm())      # 10 058 110 gradient sums
         for _ in range(3):
             train_step_embedding(t_dist, p_specs, p_labels, 1e-4)
             t_solo.forward_tail(t_solo.tail_input(p_specs), keep=True)
@@ -463,11 +476,13 @@ def run_ours(args, rank, local_rank, world):
         rows_solo = stream_inferences(m_solo, settings, audio, 16000, 1000, 100)
         bsa._dist = saved
         stream_equal = bool(np.array_equal(rows_dist, rows_solo))
-        ok = head_diff < 1e-5 and tail_rel < 1e-3 and stream_equal
+        ok = head_diff < 1e-5 and tail_rel < 1e-3 and stream_equal and head_grad_rel < 1e-5 and tail_grad_rel < 1e-4
         flags = torch.tensor([1.0 if ok else 0.0], device=dev)
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         parity = {"finetune_parity_vs_single_rank": bool(head_diff < 1e-5), "head_param_max_abs_diff_after_10_steps": head_diff,
+                  "head_gradient_sums_rel_diff_after_allreduce": head_grad_rel,
                   "phase2_parity_vs_single_rank": bool(tail_rel < 1e-3), "phase2_param_max_rel_diff_after_3_steps": tail_rel,
+                  "phase2_gradient_sums_rel_diff_after_allreduce": tail_grad_rel,
                   "streaming_sharded_equals_unsharded": stream_equal, "all_ranks_ok": bool(flags.item() == 1.0),
                   "note": "sums over shards are added by NCCL in a different order than one rank adds them: equal to fp32 rounding"}
         if flags.item() != 1.0:
