@@ -417,10 +417,12 @@ class AudioDataset:
         """One draw of reference spec_augment (:306-364): ([(f_start, f_size), ...], [(t_start, t_size), ...])."""
         p = self.spec_aug_params
         fbands, tbands = [], []
-        for _ in range(int(self.gen.integers(0, p.frequency_n_range + 1))):
+        freq_n = int(self.gen.integers(0, p.frequency_n_range + 1))      # both counts are drawn before any band (:318-323)
+        time_n = int(self.gen.integers(0, p.time_n_range + 1))
+        for _ in range(freq_n):
             size = int(self.gen.integers(1, p.frequency_max_px + 1))
             fbands.append((int(self.gen.integers(0, freq_max - size)), size))
-        for _ in range(int(self.gen.integers(0, p.time_n_range + 1))):
+        for _ in range(time_n):
             size = int(self.gen.integers(1, p.time_max_px + 1))
             tbands.append((int(self.gen.integers(0, time_max - size)), size))
         return fbands, tbands
